@@ -1,0 +1,612 @@
+// cnn.cu -- K2: sliding-patch z-normalisation + CNN forward (generic Keras-style
+// Sequential: Conv2D / MaxPooling2D / Dense with fused bias + BatchNorm affine +
+// ReLU epilogues, softmax head, non-finite override).
+//
+// Reference semantics: _get_patches (inaSpeechSegmenter/segmenter.py:76-88),
+// DnnSegmenter.__call__ (:135-179: band select :146-147, gather of `inlabel`
+// segments :156-162, keras predict :163, r[~finite] = 0.5 :175).  The network
+// itself lives only in keras_*_cnn.hdf5 (not in the reference tree), so layers
+// arrive as iss_layer_desc records (Keras channels_last semantics).
+//
+// Data layout: activations are NHWC float32 ([patch][row=time][col=mel][chan]),
+// i.e. the implicit-GEMM A operand has K = (kh, kw, cin) contiguous in cin, and
+// Keras kernels [kh][kw][cin][cout] are the row-major B operand [K][N] verbatim.
+// The 68 x nmel patches are NEVER materialised (the reference builds ~1 GB per
+// audio-hour per network): the first conv layer gathers straight from the
+// log-mel rows and applies (x - mean) / std of its patch on the fly.
+#include <math.h>
+#include <string.h>
+#include <vector>
+
+#include "iss_common.cuh"
+
+namespace {
+
+constexpr int PATCH_H = 68;            // frames per patch (segmenter.py:149)
+constexpr int PATCH_HOP = 2;           // patch hop in frames (segmenter.py:149)
+constexpr int PATCH_LFILL = PATCH_H / (2 * PATCH_HOP);     // 17 left replicas (segmenter.py:83)
+constexpr int CNN_BATCH = 2048;        // patches per layer-by-layer sweep
+
+struct Layer {
+    iss_layer_desc d;
+    int in_h, in_w, in_c;
+    int out_h, out_w, out_c;
+};
+
+}  // namespace
+
+struct iss_cnn {
+    iss_ctx *ctx;
+    std::vector<Layer> layers;
+    float *d_blob;
+    int64_t blob_len;
+    int in_h, in_w;
+    int n_classes;
+    int64_t max_act;       // largest per-patch activation (floats) over all layer outputs
+    double flops;
+    // live profiling of one layer (bench.py roofline)
+    int prof_layer = -1;
+    std::vector<cudaEvent_t> prof_ev;      // pairs: [2i] start, [2i+1] stop
+    size_t prof_used = 0;
+    double prof_flops = 0;
+};
+
+namespace {
+
+// ------------------------------------------------------------------ patch bookkeeping
+struct PatchArrays {
+    int32_t *row0;         // first log-mel row of the patch
+    float *mu, *sigma;     // float32 statistics (population std)
+    uint8_t *finite;
+};
+
+__global__ void patch_index_kernel(const int32_t *__restrict__ seg_start, const int64_t *__restrict__ seg_off,
+                                   int n_seg, int64_t n, int64_t U, int edge_left, int edge_right,
+                                   int32_t *__restrict__ row0)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int lo = 0, hi = n_seg;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (seg_off[mid] <= i) lo = mid; else hi = mid; }
+    const int64_t p = seg_start[lo] + (i - seg_off[lo]);        // padded patch index
+    int64_t j = p - (edge_left ? PATCH_LFILL : 0);              // un-replicated window index
+    if (j < 0) j = 0;
+    if (edge_right && j > U - 1) j = U - 1;
+    row0[i] = (int32_t)(j * PATCH_HOP);
+}
+
+// one warp per patch: mean / population std over the 68 x w values (np.mean / np.std, segmenter.py:82)
+__global__ void __launch_bounds__(256)
+patch_stats_kernel(const float *__restrict__ mspec, int ld, int w, int64_t n, PatchArrays pa)
+{
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const float *base = mspec + (int64_t)pa.row0[i] * ld;
+    const int cnt = PATCH_H * w;
+    double s1 = 0.0, s2 = 0.0;
+    for (int e = lane; e < cnt; e += 32) {
+        const int r = e / w, c = e - r * w;
+        const double v = (double)base[r * ld + c];
+        s1 += v; s2 += v * v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+    if (lane == 0) {
+        const double m = s1 / cnt;
+        double var = s2 / cnt - m * m;
+        if (var < 0.0) var = 0.0;
+        const float mu = (float)m, sg = (float)sqrt(var);
+        // data = (data - mean) / std: finite iff every input is finite and std > 0
+        const bool fin = isfinite(mu) && isfinite(sg) && sg > 0.0f;
+        pa.mu[i] = mu; pa.sigma[i] = sg; pa.finite[i] = fin ? 1 : 0;
+    }
+}
+
+// ------------------------------------------------------------------ implicit-GEMM conv / dense (fp32 CUDA cores)
+struct ConvArgs {
+    const float *in;        // NHWC activations, or the log-mel rows when FIRST
+    const float *w;         // [K][N]
+    const float *bias, *pre_scale, *pre_shift, *post_scale, *post_shift;
+    float *out;             // [M][N]
+    int64_t M;              // n_img * OH * OW
+    int N, K;
+    int H, W, C;            // input dims
+    int OH, OW;
+    int KH, KW, SH, SW, PT, PL;
+    int flags;
+    // FIRST only
+    int ld;
+    const int32_t *row0; const float *mu; const float *sigma;
+};
+
+constexpr int BM = 128, BK = 16;
+
+template <int BN, bool FIRST>
+__global__ void __launch_bounds__(256, 2)
+conv_gemm_f32_kernel(const ConvArgs a)
+{
+    constexpr int TM = 8, TN = BN / 16;
+    __shared__ __align__(16) float As[2][BK][BM];
+    __shared__ __align__(16) float Bs[2][BK][BN];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int64_t m0 = (int64_t)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+
+    // ---- per-thread A-gather coordinates: one output position, 8 consecutive k per tile ----
+    const int ml = tid & (BM - 1), kh2 = tid >> 7;
+    const int64_t m = m0 + ml;
+    const bool m_ok = m < a.M;
+    int ih0 = 0, iw0 = 0;
+    const float *in_img = a.in;
+    float mu = 0.f, sg = 1.f;
+    {
+        const int64_t mm = m_ok ? m : 0;
+        const int ohw = a.OH * a.OW;
+        const int64_t img = mm / ohw;
+        const int rem = (int)(mm - img * ohw);
+        const int oh = rem / a.OW, ow = rem - oh * a.OW;
+        ih0 = oh * a.SH - a.PT; iw0 = ow * a.SW - a.PL;
+        if (FIRST) { in_img = a.in + (int64_t)a.row0[img] * a.ld; mu = a.mu[img]; sg = a.sigma[img]; }
+        else in_img = a.in + img * ((int64_t)a.H * a.W * a.C);
+    }
+    const bool vecA = !FIRST && (a.C % 8 == 0);
+    const bool vecB = (a.N % 4 == 0);
+
+    float ra[8];
+    float rb[TN];
+
+    auto load_tiles = [&](int kt) {
+        const int kb = kt * BK + kh2 * 8;
+        if (vecA) {
+            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+            if (m_ok && kb < a.K) {
+                const int tap = kb / a.C, c = kb - tap * a.C;
+                const int r = tap / a.KW, s = tap - r * a.KW;
+                const int ih = ih0 + r, iw = iw0 + s;
+                if (ih >= 0 && ih < a.H && iw >= 0 && iw < a.W) {
+                    const float4 *p = reinterpret_cast<const float4 *>(in_img + ((int64_t)ih * a.W + iw) * a.C + c);
+                    v0 = __ldg(p); v1 = __ldg(p + 1);
+                }
+            }
+            ra[0] = v0.x; ra[1] = v0.y; ra[2] = v0.z; ra[3] = v0.w;
+            ra[4] = v1.x; ra[5] = v1.y; ra[6] = v1.z; ra[7] = v1.w;
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int k = kb + q;
+                float v = 0.f;
+                if (m_ok && k < a.K) {
+                    const int tap = k / a.C, c = k - tap * a.C;
+                    const int r = tap / a.KW, s = tap - r * a.KW;
+                    const int ih = ih0 + r, iw = iw0 + s;
+                    if (ih >= 0 && ih < a.H && iw >= 0 && iw < a.W) {
+                        if (FIRST) v = __fdiv_rn(__fsub_rn(__ldg(in_img + (int64_t)ih * a.ld + iw), mu), sg);
+                        else v = __ldg(in_img + ((int64_t)ih * a.W + iw) * a.C + c);
+                    }
+                }
+                ra[q] = v;
+            }
+        }
+        // B tile: BK x BN floats, 256 threads * TN
+        {
+            const int e = tid * TN;                  // element index in the tile
+            const int kk = e / BN, nn = e - kk * BN;
+            const int k = kt * BK + kk, n = n0 + nn;
+            if (vecB && k < a.K && n + TN <= a.N) {
+#pragma unroll
+                for (int q = 0; q < TN; q += 4) {
+                    const float4 v = __ldg(reinterpret_cast<const float4 *>(a.w + (int64_t)k * a.N + n + q));
+                    rb[q] = v.x; rb[q + 1] = v.y; rb[q + 2] = v.z; rb[q + 3] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < TN; ++q) rb[q] = (k < a.K && n + q < a.N) ? __ldg(a.w + (int64_t)k * a.N + n + q) : 0.f;
+            }
+        }
+    };
+    auto store_tiles = [&](int buf) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) As[buf][kh2 * 8 + q][ml] = ra[q];
+        const int e = tid * TN;
+        const int kk = e / BN, nn = e - kk * BN;
+#pragma unroll
+        for (int q = 0; q < TN; ++q) Bs[buf][kk][nn + q] = rb[q];
+    };
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    const int nkt = (a.K + BK - 1) / BK;
+    load_tiles(0);
+    store_tiles(0);
+    __syncthreads();
+    for (int kt = 0; kt < nkt; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < nkt) load_tiles(kt + 1);
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float av[TM], bv[TN];
+            const float4 a0 = *reinterpret_cast<const float4 *>(&As[buf][kk][ty * TM]);
+            const float4 a1 = *reinterpret_cast<const float4 *>(&As[buf][kk][ty * TM + 4]);
+            av[0] = a0.x; av[1] = a0.y; av[2] = a0.z; av[3] = a0.w; av[4] = a1.x; av[5] = a1.y; av[6] = a1.z; av[7] = a1.w;
+#pragma unroll
+            for (int q = 0; q < TN; q += 4) {
+                const float4 b = *reinterpret_cast<const float4 *>(&Bs[buf][kk][tx * TN + q]);
+                bv[q] = b.x; bv[q + 1] = b.y; bv[q + 2] = b.z; bv[q + 3] = b.w;
+            }
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (kt + 1 < nkt) store_tiles(buf ^ 1);
+        __syncthreads();
+    }
+
+    // ---- epilogue: bias -> affine(pre) -> relu -> affine(post) ----
+    float eb[TN], es1[TN], et1[TN], es2[TN], et2[TN];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+        const int n = n0 + tx * TN + j;
+        const bool ok = n < a.N;
+        eb[j] = (ok && (a.flags & ISS_F_BIAS)) ? a.bias[n] : 0.f;
+        es1[j] = (ok && (a.flags & ISS_F_AFFINE_PRE)) ? a.pre_scale[n] : 1.f;
+        et1[j] = (ok && (a.flags & ISS_F_AFFINE_PRE)) ? a.pre_shift[n] : 0.f;
+        es2[j] = (ok && (a.flags & ISS_F_AFFINE_POST)) ? a.post_scale[n] : 1.f;
+        et2[j] = (ok && (a.flags & ISS_F_AFFINE_POST)) ? a.post_shift[n] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int64_t mr = m0 + ty * TM + i;
+        if (mr >= a.M) continue;
+        float v[TN];
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            float x = acc[i][j] + eb[j];
+            if (a.flags & ISS_F_AFFINE_PRE) x = fmaf(x, es1[j], et1[j]);
+            if (a.flags & ISS_F_RELU) x = fmaxf(x, 0.f);
+            if (a.flags & ISS_F_SIGMOID) x = 1.f / (1.f + expf(-x));
+            if (a.flags & ISS_F_AFFINE_POST) x = fmaf(x, es2[j], et2[j]);
+            v[j] = x;
+        }
+        float *o = a.out + mr * a.N + n0 + tx * TN;
+        if (vecB && n0 + tx * TN + TN <= a.N) {
+#pragma unroll
+            for (int q = 0; q < TN; q += 4) *reinterpret_cast<float4 *>(o + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < TN; ++j) if (n0 + tx * TN + j < a.N) o[j] = v[j];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ max pooling (NHWC)
+__global__ void __launch_bounds__(256)
+maxpool_nhwc_kernel(const float *__restrict__ in, float *__restrict__ out, int64_t total, int H, int W, int C,
+                    int OH, int OW, int KH, int KW, int SH, int SW, int PT, int PL)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;       // over [img][oh][ow][c]
+    if (i >= total) return;
+    const int c = (int)(i % C);
+    int64_t r = i / C;
+    const int ow = (int)(r % OW); r /= OW;
+    const int oh = (int)(r % OH);
+    const int64_t img = r / OH;
+    float best = -INFINITY;
+    for (int y = 0; y < KH; ++y) {
+        const int ih = oh * SH - PT + y;
+        if (ih < 0 || ih >= H) continue;
+        for (int x = 0; x < KW; ++x) {
+            const int iw = ow * SW - PL + x;
+            if (iw < 0 || iw >= W) continue;
+            const float v = in[((img * H + ih) * W + iw) * C + c];
+            best = (v > best || v != v) ? v : best;        // NaN propagates like TF's max
+        }
+    }
+    out[i] = best;
+}
+
+// ------------------------------------------------------------------ softmax head + non-finite override
+__global__ void __launch_bounds__(256)
+softmax_head_kernel(const float *__restrict__ logits, const uint8_t *__restrict__ finite, int64_t n, int K,
+                    int do_softmax, float *__restrict__ probs)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *l = logits + i * K;
+    float *p = probs + i * K;
+    if (!finite[i]) {                                   // r[finite == False, :] = 0.5 (segmenter.py:175)
+        for (int k = 0; k < K; ++k) p[k] = 0.5f;
+        return;
+    }
+    if (!do_softmax) { for (int k = 0; k < K; ++k) p[k] = l[k]; return; }
+    float mx = l[0];
+    for (int k = 1; k < K; ++k) mx = fmaxf(mx, l[k]);
+    float s = 0.f;
+    float e[8];
+    for (int k = 0; k < K; ++k) { e[k] = expf(l[k] - mx); s += e[k]; }
+    for (int k = 0; k < K; ++k) p[k] = e[k] / s;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+template <bool FIRST>
+int launch_conv(const ConvArgs &a, cudaStream_t st)
+{
+    const int64_t gm = (a.M + BM - 1) / BM;
+    ISS_REQUIRE(gm < (1ll << 31), ISS_ERR_INVALID, "conv: M too large");
+    if (a.N <= 64) {
+        dim3 grid((unsigned)gm, (unsigned)((a.N + 63) / 64));
+        conv_gemm_f32_kernel<64, FIRST><<<grid, 256, 0, st>>>(a);
+    } else {
+        dim3 grid((unsigned)gm, (unsigned)((a.N + 127) / 128));
+        conv_gemm_f32_kernel<128, FIRST><<<grid, 256, 0, st>>>(a);
+    }
+    ISS_CUDA_OK(cudaGetLastError());
+    return ISS_OK;
+}
+
+}  // namespace
+
+extern "C" int iss_cnn_create(iss_ctx *ctx, const iss_layer_desc *layers, int n_layers,
+                              const float *h_blob, int64_t blob_len, int in_h, int in_w, iss_cnn **out)
+{
+    ISS_REQUIRE(ctx && layers && h_blob && out && n_layers > 0, ISS_ERR_INVALID, "iss_cnn_create: bad argument");
+    ISS_REQUIRE(in_h == PATCH_H, ISS_ERR_UNSUPPORTED, "iss_cnn_create: patch height must be %d (segmenter.py:149)", PATCH_H);
+    ISS_REQUIRE(in_w >= 1 && in_w <= ISS_NMEL, ISS_ERR_INVALID, "iss_cnn_create: in_w=%d", in_w);
+    ISS_CUDA_OK(cudaSetDevice(ctx->device));
+    iss_cnn *m = new iss_cnn();
+    m->ctx = ctx; m->d_blob = nullptr; m->blob_len = blob_len; m->in_h = in_h; m->in_w = in_w;
+    int h = in_h, w = in_w, c = 1;
+    int64_t max_act = 0;
+    double flops = 0;
+    auto off_ok = [&](int64_t off, int64_t len) { return off >= 0 && off + len <= blob_len; };
+    for (int i = 0; i < n_layers; ++i) {
+        Layer L; L.d = layers[i]; L.in_h = h; L.in_w = w; L.in_c = c;
+        const iss_layer_desc &d = L.d;
+        bool ok = true;
+        if (d.kind == ISS_LAYER_CONV2D || d.kind == ISS_LAYER_MAXPOOL) {
+            ok = d.kh >= 1 && d.kw >= 1 && d.sh >= 1 && d.sw >= 1 && d.pad_top >= 0 && d.pad_left >= 0 &&
+                 d.pad_bottom >= 0 && d.pad_right >= 0;
+            if (ok) {
+                L.out_h = (h + d.pad_top + d.pad_bottom - d.kh) / d.sh + 1;
+                L.out_w = (w + d.pad_left + d.pad_right - d.kw) / d.sw + 1;
+                ok = L.out_h >= 1 && L.out_w >= 1;
+            }
+            if (d.kind == ISS_LAYER_CONV2D) {
+                ok = ok && d.cin == c && d.cout >= 1 && off_ok(d.w_off, (int64_t)d.kh * d.kw * d.cin * d.cout);
+                L.out_c = d.cout;
+                flops += 2.0 * L.out_h * L.out_w * (double)d.kh * d.kw * d.cin * d.cout;
+            } else {
+                L.out_c = c;
+            }
+        } else if (d.kind == ISS_LAYER_DENSE) {
+            ok = d.cin == h * w * c && d.cout >= 1 && off_ok(d.w_off, (int64_t)d.cin * d.cout);
+            L.out_h = 1; L.out_w = 1; L.out_c = d.cout;
+            flops += 2.0 * (double)d.cin * d.cout;
+        } else {
+            ok = false;
+        }
+        if (ok && d.kind != ISS_LAYER_MAXPOOL) {
+            if (d.flags & ISS_F_BIAS) ok = ok && off_ok(d.bias_off, d.cout);
+            if (d.flags & ISS_F_AFFINE_PRE) ok = ok && off_ok(d.pre_scale_off, d.cout) && off_ok(d.pre_shift_off, d.cout);
+            if (d.flags & ISS_F_AFFINE_POST) ok = ok && off_ok(d.post_scale_off, d.cout) && off_ok(d.post_shift_off, d.cout);
+            if (d.flags & ISS_F_SOFTMAX) ok = ok && (i == n_layers - 1) && d.cout <= 8;
+        }
+        if (!ok) {
+            delete m;
+            iss_set_error("iss_cnn_create: layer %d (kind %d) inconsistent with input %dx%dx%d or blob", i, d.kind, h, w, c);
+            return ISS_ERR_UNSUPPORTED;
+        }
+        h = L.out_h; w = L.out_w; c = L.out_c;
+        max_act = std::max<int64_t>(max_act, (int64_t)h * w * c);
+        m->layers.push_back(L);
+    }
+    if (!(h == 1 && w == 1 && c <= 8)) {
+        delete m;
+        iss_set_error("iss_cnn_create: network must end in a Dense head with <= 8 classes (got %dx%dx%d)", h, w, c);
+        return ISS_ERR_UNSUPPORTED;
+    }
+    m->n_classes = c; m->max_act = max_act; m->flops = flops;
+    cudaError_t e = cudaMalloc(&m->d_blob, (size_t)blob_len * sizeof(float));
+    if (e != cudaSuccess) { delete m; iss_set_error("cudaMalloc blob: %s", cudaGetErrorString(e)); return ISS_ERR_NOMEM; }
+    e = cudaMemcpy(m->d_blob, h_blob, (size_t)blob_len * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(m->d_blob); delete m; iss_set_error("cudaMemcpy blob: %s", cudaGetErrorString(e)); return ISS_ERR_CUDA; }
+    *out = m;
+    return ISS_OK;
+}
+
+extern "C" int iss_cnn_destroy(iss_cnn *cnn)
+{
+    if (!cnn) return ISS_OK;
+    cudaSetDevice(cnn->ctx->device);
+    for (cudaEvent_t ev : cnn->prof_ev) cudaEventDestroy(ev);
+    if (cnn->d_blob) cudaFree(cnn->d_blob);
+    delete cnn;
+    return ISS_OK;
+}
+
+extern "C" int iss_cnn_num_classes(const iss_cnn *cnn) { return cnn ? cnn->n_classes : -1; }
+extern "C" double iss_cnn_flops_per_patch(const iss_cnn *cnn) { return cnn ? cnn->flops : 0.0; }
+
+extern "C" int64_t iss_cnn_workspace_bytes(const iss_cnn *cnn, int64_t n, int n_seg)
+{
+    if (!cnn || n < 0 || n_seg < 0) return -1;
+    const int64_t B = std::min<int64_t>(std::max<int64_t>(n, 1), CNN_BATCH);
+    int64_t bytes = 0;
+    bytes += align_up((size_t)n * 4, 256) * 3;            // row0, mu, sigma
+    bytes += align_up((size_t)n, 256);                     // finite
+    bytes += align_up((size_t)n * 8 * 4, 256);             // logits [n][<=8]
+    bytes += 2 * align_up((size_t)B * cnn->max_act * 4, 256);
+    bytes += align_up((size_t)(n_seg + 1) * 4, 256) + align_up((size_t)(n_seg + 1) * 8, 256);   // segment tables
+    return bytes;
+}
+
+extern "C" int iss_cnn_forward(iss_ctx *ctx, iss_cnn *cnn, const float *d_mspec, int64_t L, int ld,
+                               int edge_left, int edge_right,
+                               const int32_t *h_seg_start, const int32_t *h_seg_stop, int n_seg,
+                               float *d_probs, void *d_work, int64_t work_bytes, void *stream)
+{
+    ISS_REQUIRE(ctx && cnn, ISS_ERR_INVALID, "iss_cnn_forward: NULL handle");
+    ISS_REQUIRE(ld >= cnn->in_w, ISS_ERR_INVALID, "iss_cnn_forward: ld=%d < nmel=%d", ld, cnn->in_w);
+    if (n_seg <= 0) return ISS_OK;
+    ISS_REQUIRE(h_seg_start && h_seg_stop, ISS_ERR_INVALID, "iss_cnn_forward: NULL segment arrays");
+    ISS_REQUIRE(L >= PATCH_H, ISS_ERR_INVALID, "iss_cnn_forward: L=%lld < %d frames (pad short inputs first, segmenter.py:60-65)", (long long)L, PATCH_H);
+    ISS_CUDA_OK(cudaSetDevice(ctx->device));
+    cudaStream_t st = iss_stream(stream);
+    const int64_t U = (L - PATCH_H) / PATCH_HOP + 1;                      // un-replicated windows
+    const int64_t P = (edge_left ? PATCH_LFILL : 0) + U + (edge_right ? (PATCH_LFILL - 1 + (L % 2)) : 0);
+    std::vector<int64_t> off(n_seg + 1);
+    int64_t n = 0;
+    for (int s = 0; s < n_seg; ++s) {
+        ISS_REQUIRE(h_seg_start[s] >= 0 && h_seg_stop[s] >= h_seg_start[s] && h_seg_stop[s] <= P, ISS_ERR_INVALID,
+                    "iss_cnn_forward: range %d = [%d,%d) outside [0,%lld)", s, h_seg_start[s], h_seg_stop[s], (long long)P);
+        off[s] = n; n += h_seg_stop[s] - h_seg_start[s];
+    }
+    off[n_seg] = n;
+    if (n == 0) return ISS_OK;
+    ISS_REQUIRE(d_mspec && d_probs && d_work, ISS_ERR_INVALID, "iss_cnn_forward: NULL buffer");
+    ISS_REQUIRE(work_bytes >= iss_cnn_workspace_bytes(cnn, n, n_seg), ISS_ERR_INVALID,
+                "iss_cnn_forward: workspace %lld < required %lld", (long long)work_bytes, (long long)iss_cnn_workspace_bytes(cnn, n, n_seg));
+
+    // ---- carve the workspace ----
+    const int64_t B = std::min<int64_t>(n, CNN_BATCH);
+    uint8_t *p = reinterpret_cast<uint8_t *>(d_work);
+    size_t o = 0;
+    PatchArrays pa;
+    pa.row0 = reinterpret_cast<int32_t *>(p + o); o += align_up((size_t)n * 4, 256);
+    pa.mu = reinterpret_cast<float *>(p + o);     o += align_up((size_t)n * 4, 256);
+    pa.sigma = reinterpret_cast<float *>(p + o);  o += align_up((size_t)n * 4, 256);
+    pa.finite = p + o;                            o += align_up((size_t)n, 256);
+    float *logits = reinterpret_cast<float *>(p + o); o += align_up((size_t)n * 8 * 4, 256);
+    float *act[2];
+    act[0] = reinterpret_cast<float *>(p + o);    o += align_up((size_t)B * cnn->max_act * 4, 256);
+    act[1] = reinterpret_cast<float *>(p + o);    o += align_up((size_t)B * cnn->max_act * 4, 256);
+    int32_t *d_seg_start = reinterpret_cast<int32_t *>(p + o); o += align_up((size_t)(n_seg + 1) * 4, 256);
+    int64_t *d_seg_off = reinterpret_cast<int64_t *>(p + o);   o += align_up((size_t)(n_seg + 1) * 8, 256);
+    ISS_CUDA_OK(cudaMemcpyAsync(d_seg_start, h_seg_start, sizeof(int32_t) * n_seg, cudaMemcpyHostToDevice, st));
+    ISS_CUDA_OK(cudaMemcpyAsync(d_seg_off, off.data(), sizeof(int64_t) * (n_seg + 1), cudaMemcpyHostToDevice, st));
+
+    patch_index_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_seg_start, d_seg_off, n_seg, n, U, edge_left, edge_right, pa.row0);
+    patch_stats_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(d_mspec, ld, cnn->in_w, n, pa);
+    ISS_CUDA_OK(cudaGetLastError());
+    iss_count_launch(2);
+
+    const float *blob = cnn->d_blob;
+    const int K = cnn->n_classes;
+    for (int64_t b0 = 0; b0 < n; b0 += B) {
+        const int64_t nb = std::min<int64_t>(B, n - b0);
+        const float *cur = nullptr;
+        int which = 0;
+        for (size_t li = 0; li < cnn->layers.size(); ++li) {
+            const Layer &Lr = cnn->layers[li];
+            const iss_layer_desc &d = Lr.d;
+            const bool last = (li + 1 == cnn->layers.size());
+            float *dst = last ? (logits + b0 * K) : act[which];
+            const bool prof = ((int)li == cnn->prof_layer);
+            if (prof) {
+                if (cnn->prof_used + 2 > cnn->prof_ev.size()) {
+                    for (int q = 0; q < 2; ++q) {
+                        cudaEvent_t ev;
+                        ISS_CUDA_OK(cudaEventCreate(&ev));
+                        cnn->prof_ev.push_back(ev);
+                    }
+                }
+                ISS_CUDA_OK(cudaEventRecord(cnn->prof_ev[cnn->prof_used], st));
+            }
+            if (d.kind == ISS_LAYER_MAXPOOL) {
+                ISS_REQUIRE(li > 0, ISS_ERR_UNSUPPORTED, "iss_cnn_forward: pooling as first layer is not supported");
+                const int64_t total = nb * Lr.out_h * Lr.out_w * Lr.out_c;
+                maxpool_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(cur, dst, total, Lr.in_h, Lr.in_w, Lr.in_c,
+                    Lr.out_h, Lr.out_w, d.kh, d.kw, d.sh, d.sw, d.pad_top, d.pad_left);
+                ISS_CUDA_OK(cudaGetLastError());
+            } else {
+                ConvArgs a = {};
+                a.w = blob + d.w_off;
+                a.bias = (d.flags & ISS_F_BIAS) ? blob + d.bias_off : nullptr;
+                a.pre_scale = (d.flags & ISS_F_AFFINE_PRE) ? blob + d.pre_scale_off : nullptr;
+                a.pre_shift = (d.flags & ISS_F_AFFINE_PRE) ? blob + d.pre_shift_off : nullptr;
+                a.post_scale = (d.flags & ISS_F_AFFINE_POST) ? blob + d.post_scale_off : nullptr;
+                a.post_shift = (d.flags & ISS_F_AFFINE_POST) ? blob + d.post_shift_off : nullptr;
+                a.out = dst;
+                a.flags = d.flags & ~ISS_F_SOFTMAX;
+                a.N = d.cout;
+                if (d.kind == ISS_LAYER_DENSE) {
+                    a.M = nb; a.K = d.cin; a.H = 1; a.W = 1; a.C = d.cin; a.OH = 1; a.OW = 1;
+                    a.KH = 1; a.KW = 1; a.SH = 1; a.SW = 1; a.PT = 0; a.PL = 0;
+                } else {
+                    a.M = nb * Lr.out_h * Lr.out_w; a.K = d.kh * d.kw * d.cin;
+                    a.H = Lr.in_h; a.W = Lr.in_w; a.C = Lr.in_c; a.OH = Lr.out_h; a.OW = Lr.out_w;
+                    a.KH = d.kh; a.KW = d.kw; a.SH = d.sh; a.SW = d.sw; a.PT = d.pad_top; a.PL = d.pad_left;
+                }
+                int rc;
+                if (li == 0) {
+                    ISS_REQUIRE(d.kind == ISS_LAYER_CONV2D, ISS_ERR_UNSUPPORTED, "iss_cnn_forward: first layer must be Conv2D");
+                    a.in = d_mspec; a.ld = ld; a.row0 = pa.row0 + b0; a.mu = pa.mu + b0; a.sigma = pa.sigma + b0;
+                    rc = launch_conv<true>(a, st);
+                } else {
+                    a.in = cur;
+                    rc = launch_conv<false>(a, st);
+                }
+                if (rc != ISS_OK) return rc;
+            }
+            iss_count_launch();
+            if (prof) {
+                ISS_CUDA_OK(cudaEventRecord(cnn->prof_ev[cnn->prof_used + 1], st));
+                cnn->prof_used += 2;
+                if (d.kind == ISS_LAYER_CONV2D) cnn->prof_flops += 2.0 * nb * Lr.out_h * Lr.out_w * (double)d.kh * d.kw * d.cin * d.cout;
+                else if (d.kind == ISS_LAYER_DENSE) cnn->prof_flops += 2.0 * nb * (double)d.cin * d.cout;
+            }
+            cur = dst;
+            which ^= 1;
+        }
+    }
+    const Layer &head = cnn->layers.back();
+    softmax_head_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(logits, pa.finite, n, K,
+        (head.d.flags & ISS_F_SOFTMAX) ? 1 : 0, d_probs);
+    ISS_CUDA_OK(cudaGetLastError());
+    iss_count_launch();
+    return ISS_OK;
+}
+
+extern "C" int iss_cnn_profile(iss_cnn *cnn, int layer)
+{
+    ISS_REQUIRE(cnn, ISS_ERR_INVALID, "iss_cnn_profile: NULL");
+    ISS_REQUIRE(layer >= -1 && layer < (int)cnn->layers.size(), ISS_ERR_INVALID, "iss_cnn_profile: layer %d", layer);
+    cnn->prof_layer = layer;
+    cnn->prof_used = 0;
+    cnn->prof_flops = 0;
+    return ISS_OK;
+}
+
+extern "C" int iss_cnn_profile_read(iss_cnn *cnn, double *total_ms, int64_t *launches, double *flops)
+{
+    ISS_REQUIRE(cnn && total_ms && launches && flops, ISS_ERR_INVALID, "iss_cnn_profile_read: NULL");
+    ISS_CUDA_OK(cudaSetDevice(cnn->ctx->device));
+    double t = 0;
+    for (size_t i = 0; i + 1 < cnn->prof_used; i += 2) {
+        ISS_CUDA_OK(cudaEventSynchronize(cnn->prof_ev[i + 1]));
+        float ms = 0;
+        ISS_CUDA_OK(cudaEventElapsedTime(&ms, cnn->prof_ev[i], cnn->prof_ev[i + 1]));
+        t += ms;
+    }
+    *total_ms = t; *launches = (int64_t)(cnn->prof_used / 2); *flops = cnn->prof_flops;
+    cnn->prof_used = 0; cnn->prof_flops = 0;
+    return ISS_OK;
+}
+
+extern "C" int iss_cnn_num_layers(const iss_cnn *cnn) { return cnn ? (int)cnn->layers.size() : -1; }
+
+extern "C" double iss_cnn_layer_flops(const iss_cnn *cnn, int layer)
+{
+    if (!cnn || layer < 0 || layer >= (int)cnn->layers.size()) return 0.0;
+    const Layer &L = cnn->layers[layer];
+    if (L.d.kind == ISS_LAYER_CONV2D) return 2.0 * L.out_h * L.out_w * (double)L.d.kh * L.d.kw * L.d.cin * L.d.cout;
+    if (L.d.kind == ISS_LAYER_DENSE) return 2.0 * (double)L.d.cin * L.d.cout;
+    return 0.0;
+}

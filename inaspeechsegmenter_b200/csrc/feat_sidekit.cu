@@ -1,0 +1,366 @@
+// feat_sidekit.cu -- K1: fused framing -> pre-emphasis -> log-energy -> Hann ->
+// 512-point real FFT -> power -> 24-band mel -> log, one pass over the PCM.
+//
+// Reference semantics: inaSpeechSegmenter/sidekit_mfcc.py:200-237 (power_spectrum),
+// :240-275 (framing, pre_emphasis), :118-197 (trfbank), :334 (log mel); only loge
+// and mspec are produced because that is all segmenter.py:58 keeps.
+//
+// Layout: one CTA owns a tile of FR consecutive frames; the contiguous sample
+// span of the tile ((FR-1)*160+400 samples, 2.5x frame overlap) is read from HBM
+// exactly once with 16-byte vector loads and staged in shared memory together
+// with the Hann window, the FFT twiddles and the sparse mel filterbank.  Each warp
+// then processes frames independently: a 512-point real FFT is computed as a
+// 256-point complex radix-4 Stockham FFT (4 passes through a per-warp shared
+// buffer, SoA + skewed to avoid bank conflicts) followed by the even/odd split.
+// T = float: fast path; T = double: window/FFT/power in fp64 then rounded to f32,
+// which is the reference's own precision recipe (sidekit_mfcc.py:231-233).
+#include <math.h>
+#include <string.h>
+
+#include "iss_common.cuh"
+
+namespace {
+
+constexpr int FR = 64;                               // frames per CTA tile
+constexpr int NWARP = 8;
+constexpr int NTHREAD = NWARP * 32;
+constexpr int TILE_SAMPLES = (FR - 1) * ISS_HOP + ISS_WIN;   // 10480
+constexpr int ZPAD = 272;                            // 257 + skew, padded
+
+__device__ __forceinline__ int skew(int i) { return i + (i >> 5); }
+
+template <typename T> struct Tab;
+template <> struct Tab<float> {
+    static __device__ __forceinline__ const float *win(const SidekitTables *t) { return t->win32; }
+    static __device__ __forceinline__ const float *tw256(const SidekitTables *t) { return t->tw256_32; }
+    static __device__ __forceinline__ const float *tw512(const SidekitTables *t) { return t->tw512_32; }
+    static __device__ __forceinline__ float log_(float x) { return logf(x); }
+};
+template <> struct Tab<double> {
+    static __device__ __forceinline__ const double *win(const SidekitTables *t) { return t->win64; }
+    static __device__ __forceinline__ const double *tw256(const SidekitTables *t) { return t->tw256_64; }
+    static __device__ __forceinline__ const double *tw512(const SidekitTables *t) { return t->tw512_64; }
+    static __device__ __forceinline__ float log_(double x) { return (float)log(x); }
+};
+
+template <typename T>
+struct Smem {
+    float samples[TILE_SAMPLES];
+    T win[ISS_WIN];
+    T tw256[512];
+    T tw512[2 * 257 + 2];
+    float fbw[ISS_FB_MAXNNZ];
+    int fb_lo[ISS_NMEL], fb_cnt[ISS_NMEL], fb_off[ISS_NMEL];
+    T re[NWARP][ZPAD];
+    T im[NWARP][ZPAD];
+    float pw[NWARP][ZPAD];
+    double red[NWARP][2];
+};
+
+// One radix-4 Stockham pass set over a warp-private 256-point complex buffer.
+template <typename T>
+__device__ __forceinline__ void warp_fft256(T *re, T *im, const T *tw, int lane)
+{
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const int Ns = 1 << (2 * s);
+        T yr[2][4], yi[2][4];
+        int j0[2];
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const int j = lane + 32 * b;
+            const int k = j & (Ns - 1);
+            const int step = k * (64 / Ns);
+            T vr[4], vi[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int idx = skew(j + 64 * t);
+                const T xr = re[idx], xi = im[idx];
+                if (t == 0 || s == 0) { vr[t] = xr; vi[t] = xi; }
+                else {
+                    const T c = tw[2 * (t * step)], sn = tw[2 * (t * step) + 1];   // (cos, -sin)
+                    vr[t] = xr * c - xi * sn;
+                    vi[t] = xr * sn + xi * c;
+                }
+            }
+            const T a0r = vr[0] + vr[2], a0i = vi[0] + vi[2];
+            const T a1r = vr[0] - vr[2], a1i = vi[0] - vi[2];
+            const T a2r = vr[1] + vr[3], a2i = vi[1] + vi[3];
+            const T a3r = vi[1] - vi[3], a3i = -(vr[1] - vr[3]);     // (v1 - v3) * (-i)
+            yr[b][0] = a0r + a2r; yi[b][0] = a0i + a2i;
+            yr[b][1] = a1r + a3r; yi[b][1] = a1i + a3i;
+            yr[b][2] = a0r - a2r; yi[b][2] = a0i - a2i;
+            yr[b][3] = a1r - a3r; yi[b][3] = a1i - a3i;
+            j0[b] = ((j - k) << 2) + k;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int idx = skew(j0[b] + t * Ns);
+                re[idx] = yr[b][t];
+                im[idx] = yi[b][t];
+            }
+        __syncwarp();
+    }
+}
+
+template <typename T, int PCM>
+__global__ void __launch_bounds__(NTHREAD, 2)
+sidekit_features_kernel(const void *__restrict__ pcm, int64_t n_samples, int64_t n_frames,
+                        const SidekitTables *__restrict__ tabs, float *__restrict__ mspec,
+                        float *__restrict__ loge, double *__restrict__ partials, int vec_ok)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem<T> &S = *reinterpret_cast<Smem<T> *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t f0 = (int64_t)blockIdx.x * FR;
+    const int64_t s0 = f0 * ISS_HOP;
+    const int nfr = (int)min((int64_t)FR, n_frames - f0);
+    const int nsamp = (nfr - 1) * ISS_HOP + ISS_WIN;          // <= TILE_SAMPLES, all < n_samples
+
+    // ---- stage tables (L2-resident, tiny) and the tile's samples (HBM, once) ----
+    for (int i = tid; i < ISS_WIN; i += NTHREAD) S.win[i] = Tab<T>::win(tabs)[i];
+    for (int i = tid; i < 512; i += NTHREAD) S.tw256[i] = Tab<T>::tw256(tabs)[i];
+    for (int i = tid; i < 2 * 257; i += NTHREAD) S.tw512[i] = Tab<T>::tw512(tabs)[i];
+    for (int i = tid; i < tabs->nnz; i += NTHREAD) S.fbw[i] = tabs->w[i];
+    if (tid < ISS_NMEL) { S.fb_lo[tid] = tabs->lo[tid]; S.fb_cnt[tid] = tabs->cnt[tid]; S.fb_off[tid] = tabs->off[tid]; }
+
+    if (PCM == ISS_PCM_S16) {
+        const int16_t *p = reinterpret_cast<const int16_t *>(pcm) + s0;
+        if (vec_ok) {                                  // 8 samples per 16-byte load
+            const int nv = nsamp >> 3;
+            const int4 *pv = reinterpret_cast<const int4 *>(p);
+            for (int i = tid; i < nv; i += NTHREAD) {
+                const int4 v = __ldg(pv + i);
+                const int w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    S.samples[8 * i + 2 * q] = (float)(short)(w[q] & 0xffff) * (1.0f / 32768.0f);
+                    S.samples[8 * i + 2 * q + 1] = (float)(short)(w[q] >> 16) * (1.0f / 32768.0f);
+                }
+            }
+            for (int i = (nv << 3) + tid; i < nsamp; i += NTHREAD) S.samples[i] = (float)p[i] * (1.0f / 32768.0f);
+        } else {
+            for (int i = tid; i < nsamp; i += NTHREAD) S.samples[i] = (float)p[i] * (1.0f / 32768.0f);
+        }
+    } else {
+        const float *p = reinterpret_cast<const float *>(pcm) + s0;
+        if (vec_ok) {
+            const int nv = nsamp >> 2;
+            const float4 *pv = reinterpret_cast<const float4 *>(p);
+            float4 *sv = reinterpret_cast<float4 *>(S.samples);
+            for (int i = tid; i < nv; i += NTHREAD) sv[i] = __ldg(pv + i);
+            for (int i = (nv << 2) + tid; i < nsamp; i += NTHREAD) S.samples[i] = p[i];
+        } else {
+            for (int i = tid; i < nsamp; i += NTHREAD) S.samples[i] = p[i];
+        }
+    }
+    __syncthreads();
+
+    T *re = S.re[warp], *im = S.im[warp];
+    float *pw = S.pw[warp];
+    double acc_sum = 0.0, acc_cnt = 0.0;
+
+    for (int fl = warp; fl < nfr; fl += NWARP) {
+        const float *x = S.samples + fl * ISS_HOP;
+        // ---- pre-emphasis (f32, numpy op order: x - (x_prev * 0.97f)), energy, window ----
+        double e = 0.0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int n = lane + 32 * i;                 // 0..511
+            T v = (T)0;
+            if (n < ISS_WIN) {
+                const float xc = x[n];
+                const float xp = (n == 0) ? xc : x[n - 1];
+                const float y = __fsub_rn(xc, __fmul_rn(xp, 0.97f));
+                e += (double)y * (double)y;
+                v = (T)y * S.win[n];
+            }
+            // z[m] = v[2m] + i v[2m+1]
+            if (n & 1) im[skew(n >> 1)] = v; else re[skew(n >> 1)] = v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+        __syncwarp();
+
+        warp_fft256<T>(re, im, S.tw256, lane);
+
+        // ---- split the packed spectrum: X[k] = E[k] + W512^k O[k], power -> f32 ----
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            const int k = lane + 32 * i;
+            if (k <= 256) {
+                const int ka = skew(k & 255), kb = skew((256 - k) & 255);
+                const T zr = re[ka], zi = im[ka];
+                const T cr = re[kb], ci = -im[kb];                  // conj(Z[256-k])
+                const T er = (T)0.5 * (zr + cr), ei = (T)0.5 * (zi + ci);
+                const T dr = (T)0.5 * (zr - cr), di = (T)0.5 * (zi - ci);
+                const T orr = di, oi = -dr;                          // O = -i * (Z - conj)/2
+                const T c = S.tw512[2 * k], sn = S.tw512[2 * k + 1];
+                const T xr = er + (orr * c - oi * sn);
+                const T xi = ei + (orr * sn + oi * c);
+                pw[k + (k >> 5)] = (float)(xr * xr + xi * xi);
+            }
+        }
+        __syncwarp();
+
+        // ---- mel filterbank (sparse triangles) + log ----
+        const int64_t f = f0 + fl;
+        if (lane < ISS_NMEL) {
+            const int lo = S.fb_lo[lane], cnt = S.fb_cnt[lane];
+            const float *w = S.fbw + S.fb_off[lane];
+            T acc = (T)0;
+            for (int b = 0; b < cnt; ++b) {
+                const int k = lo + b;
+                acc += (T)pw[k + (k >> 5)] * (T)w[b];
+            }
+            mspec[f * ISS_NMEL + lane] = Tab<T>::log_((T)(float)acc);
+        }
+        const float le = Tab<T>::log_((T)(float)e);
+        if (lane == 0) {
+            loge[f] = le;
+            if (isfinite(le)) { acc_sum += (double)le; acc_cnt += 1.0; }
+        }
+        __syncwarp();
+    }
+
+    // ---- per-tile partial of {sum, count} of finite loge: fixed order, no atomics ----
+    if (lane == 0) { S.red[warp][0] = acc_sum; S.red[warp][1] = acc_cnt; }
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0, c = 0.0;
+#pragma unroll
+        for (int w = 0; w < NWARP; ++w) { s += S.red[w][0]; c += S.red[w][1]; }
+        partials[2 * (int64_t)blockIdx.x] = s;
+        partials[2 * (int64_t)blockIdx.x + 1] = c;
+    }
+}
+
+__global__ void __launch_bounds__(1024, 1)
+loge_stats_finalize_kernel(const double *__restrict__ partials, int64_t ntiles, double *__restrict__ stats)
+{
+    __shared__ double ss[1024], sc[1024];
+    double s = 0.0, c = 0.0;
+    for (int64_t i = threadIdx.x; i < ntiles; i += 1024) { s += partials[2 * i]; c += partials[2 * i + 1]; }
+    ss[threadIdx.x] = s; sc[threadIdx.x] = c;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) { ss[threadIdx.x] += ss[threadIdx.x + o]; sc[threadIdx.x] += sc[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { stats[0] = ss[0]; stats[1] = sc[0]; }
+}
+
+}  // namespace
+
+extern "C" int64_t iss_sidekit_num_frames(int64_t n_samples)
+{
+    if (n_samples < ISS_WIN) return 0;
+    return (n_samples - ISS_WIN) / ISS_HOP + 1;
+}
+
+extern "C" int iss_sidekit_upload_tables(iss_ctx *ctx, const float *h_fbank, const double *h_window)
+{
+    ISS_REQUIRE(ctx && h_fbank && h_window, ISS_ERR_INVALID, "iss_sidekit_upload_tables: NULL argument");
+    ISS_CUDA_OK(cudaSetDevice(ctx->device));
+    SidekitTables *t = new SidekitTables();
+    memset(t, 0, sizeof(*t));
+    int nnz = 0;
+    for (int m = 0; m < ISS_NMEL; ++m) {
+        int lo = -1, hi = -1;
+        for (int k = 0; k < ISS_NBIN; ++k)
+            if (h_fbank[m * ISS_NBIN + k] != 0.0f) { if (lo < 0) lo = k; hi = k; }
+        t->lo[m] = lo < 0 ? 0 : lo;
+        t->cnt[m] = lo < 0 ? 0 : hi - lo + 1;
+        t->off[m] = nnz;
+        if (nnz + t->cnt[m] > ISS_FB_MAXNNZ) {
+            delete t;
+            iss_set_error("iss_sidekit_upload_tables: filterbank support too wide");
+            return ISS_ERR_INVALID;
+        }
+        for (int b = 0; b < t->cnt[m]; ++b) t->w[nnz++] = h_fbank[m * ISS_NBIN + lo + b];
+    }
+    t->nnz = nnz;
+    const double PI = 3.14159265358979323846;
+    for (int i = 0; i < ISS_WIN; ++i) { t->win64[i] = h_window[i]; t->win32[i] = (float)h_window[i]; }
+    for (int m = 0; m < 256; ++m) {
+        const double c = cos(2.0 * PI * m / 256.0), s = -sin(2.0 * PI * m / 256.0);
+        t->tw256_64[2 * m] = c; t->tw256_64[2 * m + 1] = s;
+        t->tw256_32[2 * m] = (float)c; t->tw256_32[2 * m + 1] = (float)s;
+    }
+    for (int k = 0; k <= 256; ++k) {
+        const double c = cos(2.0 * PI * k / 512.0), s = -sin(2.0 * PI * k / 512.0);
+        t->tw512_64[2 * k] = c; t->tw512_64[2 * k + 1] = s;
+        t->tw512_32[2 * k] = (float)c; t->tw512_32[2 * k + 1] = (float)s;
+    }
+    if (!ctx->d_tables) {
+        cudaError_t e = cudaMalloc(&ctx->d_tables, sizeof(SidekitTables));
+        if (e != cudaSuccess) { delete t; iss_set_error("cudaMalloc tables: %s", cudaGetErrorString(e)); return ISS_ERR_NOMEM; }
+    }
+    cudaError_t e = cudaMemcpy(ctx->d_tables, t, sizeof(SidekitTables), cudaMemcpyHostToDevice);
+    delete t;
+    if (e != cudaSuccess) { iss_set_error("cudaMemcpy tables: %s", cudaGetErrorString(e)); return ISS_ERR_CUDA; }
+    ctx->tables_ready = true;
+    return ISS_OK;
+}
+
+template <typename T, int PCM>
+static int launch_features(iss_ctx *ctx, const void *d_pcm, int64_t n_samples, int64_t L, int64_t ntiles,
+                           float *d_mspec, float *d_loge, int vec_ok, cudaStream_t st)
+{
+    auto kern = sidekit_features_kernel<T, PCM>;
+    const size_t smem = sizeof(Smem<T>);
+    ISS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)ntiles, NTHREAD, smem, st>>>(d_pcm, n_samples, L, ctx->d_tables, d_mspec, d_loge,
+                                                   ctx->d_partials, vec_ok);
+    ISS_CUDA_OK(cudaGetLastError());
+    iss_count_launch();
+    return ISS_OK;
+}
+
+extern "C" int iss_sidekit_features(iss_ctx *ctx, const void *d_pcm, int pcm_format, int64_t n_samples,
+                                    int fft_precision, float *d_mspec, float *d_loge,
+                                    double *d_loge_stats, void *stream)
+{
+    ISS_REQUIRE(ctx, ISS_ERR_INVALID, "iss_sidekit_features: ctx is NULL");
+    ISS_REQUIRE(ctx->tables_ready, ISS_ERR_STATE, "iss_sidekit_features: call iss_sidekit_upload_tables first");
+    ISS_REQUIRE(pcm_format == ISS_PCM_F32 || pcm_format == ISS_PCM_S16, ISS_ERR_INVALID, "bad pcm_format %d", pcm_format);
+    ISS_REQUIRE(fft_precision == ISS_FFT_FP32 || fft_precision == ISS_FFT_FP64, ISS_ERR_INVALID, "bad fft_precision %d", fft_precision);
+    ISS_CUDA_OK(cudaSetDevice(ctx->device));
+    cudaStream_t st = iss_stream(stream);
+    const int64_t L = iss_sidekit_num_frames(n_samples);
+    if (L == 0) {
+        if (d_loge_stats) ISS_CUDA_OK(cudaMemsetAsync(d_loge_stats, 0, 2 * sizeof(double), st));
+        return ISS_OK;
+    }
+    ISS_REQUIRE(d_pcm && d_mspec && d_loge, ISS_ERR_INVALID, "iss_sidekit_features: NULL buffer");
+    const int64_t ntiles = (L + FR - 1) / FR;
+    ISS_REQUIRE(ntiles < (1ll << 31), ISS_ERR_INVALID, "iss_sidekit_features: signal too long for one call");
+    if (ntiles > ctx->partials_cap) {
+        if (ctx->d_partials) ISS_CUDA_OK(cudaFree(ctx->d_partials));
+        ctx->d_partials = nullptr; ctx->partials_cap = 0;
+        const int64_t cap = ntiles + ntiles / 2 + 1024;
+        cudaError_t e = cudaMalloc(&ctx->d_partials, (size_t)cap * 2 * sizeof(double));
+        if (e != cudaSuccess) { iss_set_error("cudaMalloc partials: %s", cudaGetErrorString(e)); return ISS_ERR_NOMEM; }
+        ctx->partials_cap = cap;
+    }
+    const int vec_ok = ((reinterpret_cast<uintptr_t>(d_pcm) & 15) == 0) ? 1 : 0;
+    int rc;
+    if (fft_precision == ISS_FFT_FP32)
+        rc = (pcm_format == ISS_PCM_S16)
+                 ? launch_features<float, ISS_PCM_S16>(ctx, d_pcm, n_samples, L, ntiles, d_mspec, d_loge, vec_ok, st)
+                 : launch_features<float, ISS_PCM_F32>(ctx, d_pcm, n_samples, L, ntiles, d_mspec, d_loge, vec_ok, st);
+    else
+        rc = (pcm_format == ISS_PCM_S16)
+                 ? launch_features<double, ISS_PCM_S16>(ctx, d_pcm, n_samples, L, ntiles, d_mspec, d_loge, vec_ok, st)
+                 : launch_features<double, ISS_PCM_F32>(ctx, d_pcm, n_samples, L, ntiles, d_mspec, d_loge, vec_ok, st);
+    if (rc != ISS_OK) return rc;
+    if (d_loge_stats) {
+        loge_stats_finalize_kernel<<<1, 1024, 0, st>>>(ctx->d_partials, ntiles, d_loge_stats);
+        ISS_CUDA_OK(cudaGetLastError());
+        iss_count_launch();
+    }
+    return ISS_OK;
+}

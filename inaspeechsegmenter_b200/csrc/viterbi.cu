@@ -1,0 +1,300 @@
+// viterbi.cu -- K3: max-sum Viterbi smoothing on device.
+//
+// Reference semantics: inaSpeechSegmenter/pyannote_viterbi.py:118-224 as called
+// from segmenter.py:72 (energy, K = 2) and :176 (CNN posteriors, K = 2 or 3):
+//   V[0,j] = E[0,j] + log(1/K);  P[t,j] = first argmax_k (V[t-1,k] + A[k,j]);
+//   V[t,j] = E[t,j] + (V[t-1,P] + A[P,j]);  backtrack from first argmax V[T-1].
+//
+// Exactness: the forward recursion is evaluated in IEEE double in exactly the
+// reference's order of operations (so every argmax decision sees the same bits);
+// that chain is inherently serial, so the forward pass runs one warp per
+// sequence: the 32 lanes fetch and convert 32 steps of emissions in parallel
+// (coalesced), then replay them through register shuffles while every lane
+// carries the same V; lane j keeps step j's back-pointer byte so stores are
+// coalesced too.  The backtrack -- pure integer function composition, hence
+// associative and exact -- is parallel: per-256-step chunk maps, a short serial
+// scan over chunk maps, then all chunks emit their states concurrently.
+#include <math.h>
+#include <vector>
+
+#include "iss_common.cuh"
+
+namespace {
+
+constexpr int CH = 256;            // backtrack chunk (steps)
+constexpr int MAXK = 4;
+
+struct VitParams {
+    double A[MAXK][MAXK];          // from -> to
+    double prior;
+    double emis_hit, emis_miss;    // energy mode
+    double log_ratio;
+};
+
+struct VitLayout {
+    uint8_t *bp;                   // [total] one byte per step: 2 bits per destination state
+    uint8_t *cmap;                 // [nchunks] composite map per chunk
+    uint8_t *cend;                 // [nchunks] state at the last step of each chunk
+    int64_t *seg_off;              // [n_seg+1]
+    int64_t *chunk_off;            // [n_seg+1]
+    uint8_t *last;                 // [n_seg] argmax V[T-1]
+};
+
+__device__ __forceinline__ bool better(double c, double best)
+{
+    // numpy.argmax: strictly greater replaces; the first NaN wins and sticks.
+    return !(c <= best) && (best == best);
+}
+
+template <int K, bool ENERGY>
+__global__ void __launch_bounds__(32)
+viterbi_forward_kernel(const float *__restrict__ src, const double *__restrict__ stats, VitParams prm, VitLayout lay)
+{
+    const int seg = blockIdx.x, lane = threadIdx.x;
+    const int64_t t0 = lay.seg_off[seg];
+    const int64_t T = lay.seg_off[seg + 1] - t0;
+    if (T <= 0) return;
+    double thr = 0.0;
+    if (ENERGY) {
+        // np.mean(f32 array) is f32; + np.log(ratio) (f64) promotes to f64 (segmenter.py:70)
+        const double cnt = stats[1];
+        const float mean32 = (float)(stats[0] / cnt);          // 0/0 -> NaN like the mean of an empty slice
+        thr = (double)mean32 + prm.log_ratio;
+    }
+    double V[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) V[j] = 0.0;
+
+    for (int64_t base = 0; base < T; base += 32) {
+        const int64_t t = base + lane;
+        double e[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) e[j] = 0.0;
+        if (t < T) {
+            if (ENERGY) {
+                const bool raw = (double)src[t0 + t] > thr;     // NaN thr -> all false
+                e[0] = raw ? prm.emis_miss : prm.emis_hit;
+                e[1] = raw ? prm.emis_hit : prm.emis_miss;
+            } else {
+#pragma unroll
+                for (int j = 0; j < K; ++j)                     // np.log on float32, correctly rounded
+                    e[j] = (double)(float)log((double)src[(t0 + t) * K + j]);
+            }
+        }
+        const int nstep = (int)min((int64_t)32, T - base);
+        unsigned mybp = 0;
+        for (int s = 0; s < nstep; ++s) {
+            double es[K];
+#pragma unroll
+            for (int j = 0; j < K; ++j) es[j] = __shfl_sync(0xffffffffu, e[j], s);
+            unsigned bp = 0;
+            if (base + s == 0) {
+#pragma unroll
+                for (int j = 0; j < K; ++j) { V[j] = es[j] + prm.prior; bp |= (unsigned)j << (2 * j); }
+            } else {
+                double Vn[K];
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    double best = V[0] + prm.A[0][j];
+                    double vn = es[j] + best;
+                    unsigned arg = 0;
+#pragma unroll
+                    for (int k = 1; k < K; ++k) {
+                        const double c = V[k] + prm.A[k][j];
+                        const double vc = es[j] + c;            // speculative: same op whichever wins
+                        const bool u = better(c, best);
+                        best = u ? c : best;
+                        vn = u ? vc : vn;
+                        arg = u ? (unsigned)k : arg;
+                    }
+                    Vn[j] = vn;
+                    bp |= arg << (2 * j);
+                }
+#pragma unroll
+                for (int j = 0; j < K; ++j) V[j] = Vn[j];
+            }
+            if (lane == s) mybp = bp;
+        }
+        if (t < T) lay.bp[t0 + t] = (uint8_t)mybp;
+    }
+    if (lane == 0) {
+        int arg = 0;
+        double best = V[0];
+#pragma unroll
+        for (int k = 1; k < K; ++k) {
+            const bool u = better(V[k], best);
+            best = u ? V[k] : best;
+            arg = u ? k : arg;
+        }
+        lay.last[seg] = (uint8_t)arg;
+    }
+}
+
+__device__ __forceinline__ int find_seg(const int64_t *chunk_off, int n_seg, int64_t c)
+{
+    int lo = 0, hi = n_seg;            // chunk_off[lo] <= c < chunk_off[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (chunk_off[mid] <= c) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// cmap[c]: (state at the last step of chunk c) -> (state at the last step of chunk c-1)
+__global__ void viterbi_chunk_map_kernel(VitLayout lay, int n_seg, int64_t nchunks)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchunks) return;
+    const int seg = find_seg(lay.chunk_off, n_seg, c);
+    const int64_t t0 = lay.seg_off[seg], T = lay.seg_off[seg + 1] - t0;
+    const int64_t lc = c - lay.chunk_off[seg];
+    const int64_t a = lc * CH, b = min(a + CH, T);          // steps [a, b)
+    unsigned m = 0xE4;                                      // identity: 3,2,1,0 in 2-bit fields
+    const uint8_t *bp = lay.bp + t0;
+    for (int64_t t = b - 1; t >= a; --t) {
+        if (t == 0) break;                                  // bp[0] is unused (no predecessor)
+        const unsigned f = bp[t];
+        unsigned r = 0;
+#pragma unroll
+        for (int x = 0; x < 4; ++x) r |= ((f >> (2 * ((m >> (2 * x)) & 3))) & 3) << (2 * x);
+        m = r;
+    }
+    lay.cmap[c] = (uint8_t)m;
+}
+
+// serial over the chunks of one segment (T/256 steps), one thread per segment
+__global__ void viterbi_chunk_scan_kernel(VitLayout lay, int n_seg)
+{
+    const int seg = blockIdx.x * blockDim.x + threadIdx.x;
+    if (seg >= n_seg) return;
+    const int64_t c0 = lay.chunk_off[seg], c1 = lay.chunk_off[seg + 1];
+    if (c1 <= c0) return;
+    unsigned x = lay.last[seg];
+    for (int64_t c = c1 - 1; c >= c0; --c) {
+        lay.cend[c] = (uint8_t)x;
+        x = (lay.cmap[c] >> (2 * x)) & 3;
+    }
+}
+
+__global__ void viterbi_chunk_emit_kernel(VitLayout lay, int n_seg, int64_t nchunks, int out_stride,
+                                          uint8_t *__restrict__ states)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchunks) return;
+    const int seg = find_seg(lay.chunk_off, n_seg, c);
+    const int64_t t0 = lay.seg_off[seg], T = lay.seg_off[seg + 1] - t0;
+    const int64_t lc = c - lay.chunk_off[seg];
+    const int64_t a = lc * CH, b = min(a + CH, T);
+    const uint8_t *bp = lay.bp + t0;
+    unsigned x = lay.cend[c];
+    for (int64_t t = b - 1; t >= a; --t) {
+        if (out_stride == 1) states[t0 + t] = (uint8_t)x;
+        else if (t % out_stride == 0) states[(t0 + t) / out_stride] = (uint8_t)x;   // single sequence (t0 == 0)
+        x = (bp[t] >> (2 * x)) & 3;
+    }
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct HostPlan {
+    std::vector<int64_t> seg_off, chunk_off;
+    int64_t total, nchunks;
+};
+
+int make_layout(const int64_t *h_seg_off, int n_seg, void *d_work, HostPlan &hp, VitLayout &lay, cudaStream_t st)
+{
+    hp.seg_off.assign(h_seg_off, h_seg_off + n_seg + 1);
+    hp.chunk_off.resize(n_seg + 1);
+    int64_t nc = 0;
+    for (int s = 0; s < n_seg; ++s) {
+        hp.chunk_off[s] = nc;
+        const int64_t T = h_seg_off[s + 1] - h_seg_off[s];
+        ISS_REQUIRE(T >= 0, ISS_ERR_INVALID, "viterbi: segment offsets must be non-decreasing");
+        nc += (T + CH - 1) / CH;
+    }
+    hp.chunk_off[n_seg] = nc;
+    hp.total = h_seg_off[n_seg];
+    hp.nchunks = nc;
+    uint8_t *p = reinterpret_cast<uint8_t *>(d_work);
+    size_t o = 0;
+    lay.bp = p + o;        o = align_up(o + (size_t)hp.total, 256);
+    lay.cmap = p + o;      o = align_up(o + (size_t)nc, 256);
+    lay.cend = p + o;      o = align_up(o + (size_t)nc, 256);
+    lay.seg_off = reinterpret_cast<int64_t *>(p + o);   o = align_up(o + sizeof(int64_t) * (n_seg + 1), 256);
+    lay.chunk_off = reinterpret_cast<int64_t *>(p + o); o = align_up(o + sizeof(int64_t) * (n_seg + 1), 256);
+    lay.last = p + o;
+    ISS_CUDA_OK(cudaMemcpyAsync(lay.seg_off, hp.seg_off.data(), sizeof(int64_t) * (n_seg + 1), cudaMemcpyHostToDevice, st));
+    ISS_CUDA_OK(cudaMemcpyAsync(lay.chunk_off, hp.chunk_off.data(), sizeof(int64_t) * (n_seg + 1), cudaMemcpyHostToDevice, st));
+    return ISS_OK;
+}
+
+int run_backtrack(const VitLayout &lay, const HostPlan &hp, int n_seg, int out_stride, uint8_t *d_states, cudaStream_t st)
+{
+    if (hp.nchunks == 0) return ISS_OK;
+    const int TB = 128;
+    const unsigned gc = (unsigned)((hp.nchunks + TB - 1) / TB);
+    viterbi_chunk_map_kernel<<<gc, TB, 0, st>>>(lay, n_seg, hp.nchunks);
+    viterbi_chunk_scan_kernel<<<(n_seg + 63) / 64, 64, 0, st>>>(lay, n_seg);
+    viterbi_chunk_emit_kernel<<<gc, TB, 0, st>>>(lay, n_seg, hp.nchunks, out_stride, d_states);
+    ISS_CUDA_OK(cudaGetLastError());
+    iss_count_launch(3);
+    return ISS_OK;
+}
+
+}  // namespace
+
+extern "C" int64_t iss_viterbi_work_bytes(int64_t total_steps, int n_seg)
+{
+    if (total_steps < 0 || n_seg < 0) return -1;
+    const int64_t nc = total_steps / CH + n_seg + 1;
+    return total_steps + 2 * nc + 2 * (int64_t)sizeof(int64_t) * (n_seg + 1) + n_seg + 8 * 256;
+}
+
+extern "C" int iss_energy_viterbi(iss_ctx *ctx, const float *d_loge, int64_t L, const double *d_loge_stats,
+                                  double log_ratio, const double *h_emis, const double *h_trans,
+                                  double log_prior, int out_stride, uint8_t *d_states, void *d_work,
+                                  void *stream)
+{
+    ISS_REQUIRE(ctx && h_emis && h_trans, ISS_ERR_INVALID, "iss_energy_viterbi: NULL argument");
+    ISS_REQUIRE(out_stride >= 1, ISS_ERR_INVALID, "iss_energy_viterbi: out_stride must be >= 1");
+    if (L <= 0) return ISS_OK;
+    ISS_REQUIRE(d_loge && d_loge_stats && d_states && d_work, ISS_ERR_INVALID, "iss_energy_viterbi: NULL buffer");
+    ISS_CUDA_OK(cudaSetDevice(ctx->device));
+    cudaStream_t st = iss_stream(stream);
+    const int64_t off[2] = {0, L};
+    HostPlan hp; VitLayout lay;
+    int rc = make_layout(off, 1, d_work, hp, lay, st);
+    if (rc != ISS_OK) return rc;
+    VitParams prm = {};
+    for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) prm.A[i][j] = h_trans[i * 2 + j];
+    prm.prior = log_prior; prm.emis_hit = h_emis[0]; prm.emis_miss = h_emis[1]; prm.log_ratio = log_ratio;
+    viterbi_forward_kernel<2, true><<<1, 32, 0, st>>>(d_loge, d_loge_stats, prm, lay);
+    ISS_CUDA_OK(cudaGetLastError());
+    iss_count_launch();
+    return run_backtrack(lay, hp, 1, out_stride, d_states, st);
+}
+
+extern "C" int iss_viterbi_segments(iss_ctx *ctx, const float *d_probs, int K, const int64_t *h_seg_off,
+                                    int n_seg, const double *h_trans, double log_prior, uint8_t *d_states,
+                                    void *d_work, void *stream)
+{
+    ISS_REQUIRE(ctx && h_seg_off && h_trans, ISS_ERR_INVALID, "iss_viterbi_segments: NULL argument");
+    ISS_REQUIRE(K >= 2 && K <= MAXK, ISS_ERR_UNSUPPORTED, "iss_viterbi_segments: K=%d not in [2,4]", K);
+    if (n_seg <= 0 || h_seg_off[n_seg] == 0) return ISS_OK;
+    ISS_REQUIRE(d_probs && d_states && d_work, ISS_ERR_INVALID, "iss_viterbi_segments: NULL buffer");
+    ISS_CUDA_OK(cudaSetDevice(ctx->device));
+    cudaStream_t st = iss_stream(stream);
+    HostPlan hp; VitLayout lay;
+    int rc = make_layout(h_seg_off, n_seg, d_work, hp, lay, st);
+    if (rc != ISS_OK) return rc;
+    VitParams prm = {};
+    for (int i = 0; i < K; ++i) for (int j = 0; j < K; ++j) prm.A[i][j] = h_trans[i * K + j];
+    prm.prior = log_prior;
+    // shift the views so that segment offsets index d_probs rows directly
+    if (K == 2) viterbi_forward_kernel<2, false><<<n_seg, 32, 0, st>>>(d_probs, nullptr, prm, lay);
+    else if (K == 3) viterbi_forward_kernel<3, false><<<n_seg, 32, 0, st>>>(d_probs, nullptr, prm, lay);
+    else viterbi_forward_kernel<4, false><<<n_seg, 32, 0, st>>>(d_probs, nullptr, prm, lay);
+    ISS_CUDA_OK(cudaGetLastError());
+    iss_count_launch();
+    return run_backtrack(lay, hp, n_seg, 1, d_states, st);
+}

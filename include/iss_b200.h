@@ -1,0 +1,187 @@
+/* iss_b200.h -- C ABI of libiss_b200.so: the B200 (sm_100a) implementation of
+ * inaSpeechSegmenter's per-frame hot path.
+ *
+ * The reference (ina-foss/inaSpeechSegmenter) is pure Python and has no FFI;
+ * its seams are Python call signatures.  Every entry point below names the
+ * reference call it replaces (path:line relative to the reference tree).
+ * Conventions:
+ *   - plain C types only; all `d_*` pointers are DEVICE pointers owned by the
+ *     caller (e.g. torch.Tensor.data_ptr()), `h_*` pointers are HOST pointers;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *     calls are asynchronous on that stream unless stated otherwise;
+ *   - return value: 0 = ISS_OK, negative = error; iss_last_error() returns a
+ *     thread-local message for the last failing call on this thread;
+ *   - handles are opaque; distinct contexts may be used concurrently from
+ *     different host threads (the reference extracts features on a worker
+ *     thread while the main thread runs the CNNs, segmenter.py:377-387);
+ *   - there is NO CPU fallback anywhere behind this ABI.
+ */
+#ifndef ISS_B200_H
+#define ISS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ISS_OK              0
+#define ISS_ERR_INVALID    -1   /* bad argument */
+#define ISS_ERR_CUDA       -2   /* a CUDA runtime call failed */
+#define ISS_ERR_NOMEM      -3
+#define ISS_ERR_UNSUPPORTED -4  /* e.g. layer type / shape the kernels do not cover */
+#define ISS_ERR_STATE      -5   /* tables not uploaded, model not loaded, ... */
+
+typedef struct iss_ctx iss_ctx;
+typedef struct iss_cnn iss_cnn;
+typedef struct iss_resnet iss_resnet;
+
+/* ---- library / context ------------------------------------------------- */
+
+int         iss_version(void);               /* ABI version, currently 1 */
+const char *iss_last_error(void);
+/* Creates a context bound to CUDA device `device` (one per host thread that
+ * issues work).  Fails with ISS_ERR_CUDA if the device is not compute
+ * capability 10.x. */
+int iss_ctx_create(int device, iss_ctx **out);
+int iss_ctx_destroy(iss_ctx *ctx);
+/* Number of kernels this library has launched in this process so far (all
+ * contexts); bench.py reports the delta over its timed region. */
+int64_t iss_launch_count(void);
+
+/* ---- K1: SIDEKIT log-mel + log-energy front-end -------------------------
+ * Replaces mfcc(sig, get_mspec=True) as used by _media2feats
+ * (inaSpeechSegmenter/sidekit_mfcc.py:278-352 via segmenter.py:53-58):
+ * framing 400/160 (:240-263), per-frame pre-emphasis 0.97 (:266-275),
+ * loge = log(sum y^2) before windowing (:226), Hann(400) (:223), 512-point
+ * real FFT power (:232-233), 24-band mel filterbank (:118-197) and log (:334).
+ * The dead DCT (:337) is not computed. */
+
+#define ISS_PCM_F32 0   /* float32 samples in [-1, 1) (what soundfile returns, io.py:51) */
+#define ISS_PCM_S16 1   /* int16 PCM; converted as s / 32768.0f, exactly what soundfile does */
+
+#define ISS_FFT_FP32 0  /* single-precision FFT (fast) */
+#define ISS_FFT_FP64 1  /* double-precision window + FFT, power rounded to f32: the
+                           reference's own precision recipe (sidekit_mfcc.py:231-233) */
+
+/* L = int((n - 400) / 160) + 1 frames, 0 if n < 400 (sidekit_mfcc.py:254). */
+int64_t iss_sidekit_num_frames(int64_t n_samples);
+
+/* Host-precomputed tables: fbank = trfbank(16000,512,100,8000,0,24)[0]
+ * (float32 [24][257], sidekit_mfcc.py:332) and window = numpy.hanning(400)
+ * (float64 [400], :223).  Must be called once per context before
+ * iss_sidekit_features.  Synchronous. */
+int iss_sidekit_upload_tables(iss_ctx *ctx, const float *h_fbank, const double *h_window);
+
+/* d_pcm: n_samples samples (format pcm_format) in device memory.
+ * d_mspec: float32 [L][24]; d_loge: float32 [L];
+ * d_loge_stats: double[2] = { sum of finite loge, count of finite loge } --
+ * the global reduction _energy_activity needs (segmenter.py:70); written by a
+ * deterministic two-stage reduction (no atomics).  A time-shard passes a
+ * pointer to its own first sample (frame f starts at sample 160*f); int16
+ * input needs 2-byte and float input 4-byte alignment only. */
+int iss_sidekit_features(iss_ctx *ctx, const void *d_pcm, int pcm_format, int64_t n_samples,
+                         int fft_precision, float *d_mspec, float *d_loge,
+                         double *d_loge_stats, void *stream);
+
+/* ---- K3: Viterbi smoothing ------------------------------------------------
+ * Replaces viterbi_decoding(emission, transition) for the two ways the hot
+ * path calls it (inaSpeechSegmenter/pyannote_viterbi.py:118-224; callers
+ * segmenter.py:72 and :176).  Exact IEEE-double max-sum recursion in the
+ * reference's evaluation order, first-max tie break, uniform prior log(1/K). */
+
+/* Energy activity (segmenter.py:69-73 + viterbi_utils.py:29-42):
+ *   thr   = (double)(float)(stats[0]/stats[1]) + log_ratio   (NaN if count == 0)
+ *   raw_t = (double)loge[t] > thr
+ *   E_t   = { raw_t ? h_emis[1] : h_emis[0],  raw_t ? h_emis[0] : h_emis[1] }
+ *           with h_emis = { log(1-1e-10), log(1e-10) } computed by the host the
+ *           way the reference does (numpy), A = h_trans (row-major [2][2],
+ *           from->to), prior = log_prior = log(1/2).
+ * d_states: uint8 [ceil(L / out_stride)] -- state of every out_stride-th frame
+ * (the reference keeps [::2], segmenter.py:262).  d_work: scratch of at least
+ * iss_viterbi_work_bytes(L, 1) bytes. */
+int iss_energy_viterbi(iss_ctx *ctx, const float *d_loge, int64_t L, const double *d_loge_stats,
+                       double log_ratio, const double *h_emis, const double *h_trans,
+                       double log_prior, int out_stride, uint8_t *d_states, void *d_work,
+                       void *stream);
+
+/* Batched decode of CNN posteriors (segmenter.py:167-178): for segment s the
+ * rows d_probs[seg_off[s] .. seg_off[s+1]) (float32 [n][K], already carrying
+ * the 0.5 override of :175) are turned into emissions log(p) (float32 log,
+ * widened to double like numpy's promotion) and decoded independently with a
+ * fresh uniform prior log_prior = log(1/K).  h_seg_off: n_seg+1 int64 host
+ * offsets.  2 <= K <= 4.  d_states: uint8 [n]. */
+int iss_viterbi_segments(iss_ctx *ctx, const float *d_probs, int K, const int64_t *h_seg_off,
+                         int n_seg, const double *h_trans, double log_prior, uint8_t *d_states,
+                         void *d_work, void *stream);
+int64_t iss_viterbi_work_bytes(int64_t total_steps, int n_seg);
+
+/* ---- K2: patch z-normalisation + CNN forward ------------------------------
+ * Replaces _get_patches (segmenter.py:76-88) + keras Model.predict
+ * (segmenter.py:131-133,163) + the non-finite override (:175). */
+
+#define ISS_LAYER_CONV2D  1
+#define ISS_LAYER_DENSE   2
+#define ISS_LAYER_MAXPOOL 3
+
+#define ISS_F_BIAS        1   /* + bias[cout] */
+#define ISS_F_AFFINE_PRE  2   /* then  x*pre_scale[c] + pre_shift[c]   (BatchNorm before the activation) */
+#define ISS_F_RELU        4   /* then  max(x, 0) */
+#define ISS_F_AFFINE_POST 8   /* then  x*post_scale[c] + post_shift[c] (BatchNorm after the activation) */
+#define ISS_F_SOFTMAX     16  /* softmax over cout (last layer only) */
+#define ISS_F_SIGMOID     32
+
+typedef struct iss_layer_desc {
+    int32_t kind;                 /* ISS_LAYER_* */
+    int32_t kh, kw;               /* kernel / pool window (rows = time, cols = mel band) */
+    int32_t sh, sw;               /* strides */
+    int32_t pad_top, pad_left, pad_bottom, pad_right;  /* zero (conv) / -inf (pool) padding */
+    int32_t cin, cout;            /* DENSE: cin = flattened (H*W*C, Keras channels_last order) */
+    int32_t flags;                /* ISS_F_* */
+    int64_t w_off;                /* float offsets into the weight blob; -1 when unused.     */
+    int64_t bias_off;             /* CONV2D kernel is [kh][kw][cin][cout] (Keras layout),     */
+    int64_t pre_scale_off, pre_shift_off;    /* DENSE kernel is [cin][cout].                */
+    int64_t post_scale_off, post_shift_off;
+} iss_layer_desc;
+
+/* Builds a model for input patches of in_h x in_w x 1 (68 x nmel).  The blob is
+ * copied to the device.  Synchronous. */
+int iss_cnn_create(iss_ctx *ctx, const iss_layer_desc *layers, int n_layers,
+                   const float *h_blob, int64_t blob_len, int in_h, int in_w, iss_cnn **out);
+int iss_cnn_destroy(iss_cnn *cnn);
+int iss_cnn_num_classes(const iss_cnn *cnn);
+double iss_cnn_flops_per_patch(const iss_cnn *cnn);     /* 2 * MACs of all conv/dense layers */
+/* scratch needed by iss_cnn_forward for `n` patches in `n_seg` index ranges
+ * (activations ping-pong, patch statistics, index map). */
+int64_t iss_cnn_workspace_bytes(const iss_cnn *cnn, int64_t n, int n_seg);
+
+/* d_mspec: float32 [L][ld] log-mel rows (ld = 24; the first in_w bands are
+ * used, segmenter.py:146-147).  Patch p (0 <= p < ceil(L/2)) is frames
+ * 2*clamp(p-17, 0, U-1) .. +67 with U = (L-68)/2+1 un-replicated windows
+ * (edge replication of segmenter.py:83-85); edge_left/edge_right = 0 disable
+ * the replication on that side for a time-shard that is not at a file end
+ * (then patch p is frames 2p .. 2p+67 and p < U).
+ * The patches evaluated are those of the index ranges
+ * [h_seg_start[s], h_seg_stop[s]) concatenated (segmenter.py:156-162).
+ * d_probs: float32 [n][K] softmax, rows of non-finite patches forced to 0.5
+ * (segmenter.py:175).  n = sum of range lengths. */
+int iss_cnn_forward(iss_ctx *ctx, iss_cnn *cnn, const float *d_mspec, int64_t L, int ld,
+                    int edge_left, int edge_right,
+                    const int32_t *h_seg_start, const int32_t *h_seg_stop, int n_seg,
+                    float *d_probs, void *d_work, int64_t work_bytes, void *stream);
+
+/* Live roofline support: record CUDA events around every launch of layer
+ * `layer` (index into the iss_layer_desc list; -1 switches profiling off) on
+ * the stream the launch uses.  iss_cnn_profile_read synchronises those events,
+ * returns the summed device time (ms), the number of launches and the FLOPs
+ * those launches performed, and resets the accumulators. */
+int iss_cnn_profile(iss_cnn *cnn, int layer);
+int iss_cnn_profile_read(iss_cnn *cnn, double *total_ms, int64_t *launches, double *flops);
+/* FLOPs of one layer for one patch (2 * MACs); 0 for pooling. */
+double iss_cnn_layer_flops(const iss_cnn *cnn, int layer);
+int iss_cnn_num_layers(const iss_cnn *cnn);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISS_B200_H */

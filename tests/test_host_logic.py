@@ -1,0 +1,137 @@
+"""CPU: host-side logic of the product (no GPU, no compute through the ABI)."""
+import ctypes
+import io
+import os
+import re
+
+import numpy as np
+import pytest
+
+from inaspeechsegmenter_b200 import _lib, export_funcs, models
+from inaspeechsegmenter_b200 import io as iss_io
+from inaspeechsegmenter_b200.segmenter import _rle
+from inaspeechsegmenter_b200.sidekit_mfcc import trfbank_htk24
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _csv_rows(path):
+    rows = []
+    with open(path) as f:
+        next(f)
+        for line in f:
+            lab, a, b = line.rstrip('\n').split('\t')
+            rows.append((lab, float(a), float(b)))
+    return rows
+
+
+def test_abi_exports_every_declared_symbol():
+    """The C-ABI library loads and exports every function include/iss_b200.h declares."""
+    hdr = open(os.path.join(ROOT, 'include', 'iss_b200.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    declared = set(re.findall(r'\b(iss_[a-z0-9_]+)\s*\(', hdr))
+    assert len(declared) >= 15
+    lib = ctypes.CDLL(_lib.lib_path()) if os.path.exists(_lib.lib_path()) else _lib.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), 'libiss_b200.so does not export %s' % name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert _lib.load().iss_version() == 1
+    assert _lib.load().iss_sidekit_num_frames(1192367) == 7450      # musanmix.wav
+    assert _lib.load().iss_sidekit_num_frames(399) == 0
+
+
+def test_layer_desc_abi_layout():
+    assert ctypes.sizeof(_lib.LayerDesc) == 12 * 4 + 6 * 8
+
+
+def test_filterbank_table_matches_reference(golden):
+    assert np.array_equal(trfbank_htk24(), golden['fbank'])
+
+
+def test_csv_export_bytes(media, tmp_path):
+    for name in ('musanmix-smn-gender.csv', 'musanmix-sm-gender.csv', '0021-smn-gender.csv', 'silence2sec-smn-gender.csv'):
+        ref = os.path.join(media, name)
+        rows = _csv_rows(ref)
+        out = tmp_path / name
+        export_funcs.seg2csv(rows, str(out))
+        assert out.read_bytes() == open(ref, 'rb').read()
+    # the doubles the reference prints come from start_sec + idx * .02 (segmenter.py:276)
+    assert export_funcs.seg2csv([('noEnergy', 0 + 1124 * .02, 0 + 1454 * .02)]).split('\n')[1] == 'noEnergy\t22.48\t29.080000000000002'
+
+
+def test_csv_export_matches_pandas():
+    pd = pytest.importorskip('pandas')
+    lseg = [('music', 0 + i * .02, 0 + (i + 7) * .02) for i in range(0, 4000, 7)] + [('male', 0, 0.66)]
+    df = pd.DataFrame.from_records(lseg, columns=['labels', 'start', 'stop'])
+    assert df.to_csv(None, sep='\t', index=False) == export_funcs.seg2csv(lseg)
+
+
+def test_textgrid_export_bytes(media, tmp_path):
+    rows = _csv_rows(os.path.join(media, 'musanmix-smn-gender.csv'))
+    out = tmp_path / 'x.TextGrid'
+    export_funcs.seg2textgrid(rows, str(out))
+    assert out.read_bytes() == open(os.path.join(media, 'musanmix-smn-gender.TextGrid'), 'rb').read()
+
+
+def test_rle():
+    assert _rle(np.array([5] * 5 + [7] * 10 + [1] * 5)) == [(5, 0, 5), (7, 5, 15), (1, 15, 20)]
+    assert _rle(np.array([3])) == [(3, 0, 1)]
+
+
+def test_wav_reader(media):
+    s16 = iss_io.media2sig16kmono(os.path.join(media, 'musanmix.wav'), ffmpeg=None, dtype='float32')
+    assert s16.dtype == np.float32 and len(s16) == 1192367
+    raw = iss_io.media2sig16kmono(os.path.join(media, 'musanmix.wav'), ffmpeg=None, dtype='float32', return_int16=True)
+    assert raw.dtype == np.int16 and np.array_equal(raw.astype(np.float32) / np.float32(32768), s16)
+    f32 = iss_io.media2sig16kmono(os.path.join(media, 'lamartine.wav'), ffmpeg=None, dtype='float64')
+    assert f32.dtype == np.float64 and len(f32) == 234282
+    with pytest.raises(NotImplementedError):
+        iss_io.media2sig16kmono('x.wav', start_sec=1, ffmpeg=None)
+    with pytest.raises(NotImplementedError):
+        iss_io.media2sig16kmono('http://x/y.wav', ffmpeg=None)
+
+
+def test_lowering_fuses_bn_relu(synth_models):
+    cfg, w = synth_models['smn']
+    low = models.lower_keras_model(cfg, w, 68, 21)
+    kinds = [d['kind'] for d in low.descs]
+    assert kinds == [1, 1, 3, 1, 1, 3, 2, 2, 2]
+    conv = low.descs[0]
+    assert conv['flags'] == _lib.F_BIAS | _lib.F_AFFINE_PRE | _lib.F_RELU and (conv['kh'], conv['kw'], conv['cout']) == (4, 5, 64)
+    assert low.descs[-1]['flags'] & _lib.F_SOFTMAX and low.n_classes == 3
+    assert all(d['w_off'] % 4 == 0 for d in low.descs if d['kind'] != 3)
+    nparam = sum(v.size for k, v in w.items())
+    assert 1.0e6 < nparam < 2.0e6
+
+
+def test_lowering_rejects_unknown_layer(synth_models):
+    cfg, w = synth_models['sm']
+    bad = {'class_name': 'Sequential', 'config': {'layers': cfg['config']['layers'] + [{'class_name': 'LSTM', 'config': {'name': 'l'}}]}}
+    with pytest.raises(NotImplementedError):
+        models.lower_keras_model(bad, w, 68, 21)
+
+
+def test_npz_roundtrip(tmp_path, synth_models):
+    cfg, w = synth_models['gender']
+    p = str(tmp_path / 'm.npz')
+    models.save_npz(p, cfg, w)
+    cfg2, w2 = models.load_npz(p)
+    assert cfg2 == cfg and set(w2) == set(w) and all(np.array_equal(w[k], w2[k]) for k in w)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, 'inaspeechsegmenter_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh')):
+                src = open(os.path.join(dirpath, f)).read()
+                assert 'import oracle' not in src and 'from oracle' not in src, f
+
+
+def test_segmenter_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from inaspeechsegmenter_b200 import Segmenter
+    with pytest.raises(_lib.IssError):
+        Segmenter(ffmpeg=None, models={})
