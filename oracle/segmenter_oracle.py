@@ -125,7 +125,7 @@ class DnnSegmenterOracle:
         if batch:
             batch = np.expand_dims(np.concatenate(batch), 3)
             rawpred = np.array(self.predict(batch.astype(np.float32)), dtype=np.float32)
-            self.last_probs = rawpred.copy()
+            self.last_probs = rawpred          # the 0.5 override below edits it in place (views)
         ret = []
         for lab, a, b in lseg:
             if lab != self.inlabel:

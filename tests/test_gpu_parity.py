@@ -91,7 +91,7 @@ def test_k1_int16_equals_float32_input(rt):
 def test_k1_unaligned_and_tiny_inputs(rt):
     from oracle import sidekit_oracle as sk
     s16 = synth_audio(3, seed=9)
-    base = torch.from_numpy(np.concatenate(([0], s16))).cuda()
+    base = torch.from_numpy(np.concatenate((np.zeros(1, np.int16), s16))).cuda()
     for n in (400, 401, 559, 560, 719, 720, 10479, 10480, 10481, 16000 * 3):
         view = base[1:1 + n]                       # 2-byte aligned only
         mspec, loge, stats = rt['fe'](view, rt['lib'].FFT_FP64)
