@@ -6,10 +6,11 @@
 One step = one pass of the whole hot path (K1 log-mel/energy -> energy Viterbi
 -> smn CNN -> Viterbi -> gender CNN -> Viterbi -> segment list on the host) over
 one batch of synthetic 16 kHz mono int16 audio: BASELINE.json configs[1]
-("smn+gender on 10 h synthetic, 1xB200").  With N > 1 ranks (torchrun) every
-rank segments its own 10 h recording (the reference's only parallelism is
-file-level; no data-path collective) => weak scaling; the timed
-region is bracketed by barrier + synchronize and the max over ranks is reported.
+("smn+gender on 10 h synthetic, 1xB200").  With N > 1 ranks (torchrun) ONE recording
+of N x 10 h is time-sharded over the ranks (inaspeechsegmenter_b200/shard.py:
+34-frame halo, NCCL all-gather of loge and of the CNN posteriors, BASELINE
+configs[4]) => weak scaling (per-GPU work fixed); the timed region is bracketed
+by barrier + synchronize and the max over ranks is reported.
 
 `--impl reference` times the reference's CPU path (the numpy/torch-CPU oracle
 port: TensorFlow and the .hdf5 networks are not installable here) on the host
@@ -82,10 +83,17 @@ def synth_block_torch(torch, block, seconds, device):
     return torch.clamp(torch.round(out * 32768), -32768, 32767).to(torch.int16)
 
 
-def synth_recording(torch, hours, device, rank=0):
-    nblocks = max(1, int(round(hours * 6)))
-    sec = hours * 3600.0 / nblocks
-    return torch.cat([synth_block_torch(torch, rank * 100000 + b, sec, device) for b in range(nblocks)])
+BLOCK_SEC = 600.0
+
+
+def synth_range(torch, sa, sb, device):
+    """Samples [sa, sb) of the (arbitrarily long) synthetic recording made of 10-minute blocks."""
+    bl = int(BLOCK_SEC * SR)
+    parts = []
+    for b in range(sa // bl, (sb - 1) // bl + 1):
+        blk = synth_block_torch(torch, b, BLOCK_SEC, device)
+        parts.append(blk[max(sa - b * bl, 0):min(sb - b * bl, bl)])
+    return torch.cat(parts)
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -162,9 +170,8 @@ def make_models():
 def cpu_sample(args):
     """Host copy of the first cpu-sample-sec seconds of rank 0's recording (generated on CPU torch)."""
     import torch
-    s16 = synth_block_torch(torch, 0, args.hours * 3600.0 / max(1, int(round(args.hours * 6))), 'cpu')
     n = int(args.cpu_sample_sec * SR)
-    s16 = s16[:n].numpy()
+    s16 = synth_range(torch, 0, n, 'cpu').numpy()
     return s16.astype(np.float32) / np.float32(32768)
 
 
@@ -212,11 +219,15 @@ def run_b200(args):
     mods = make_models()
     seg = Segmenter(vad_engine='smn', detect_gender=True, ffmpeg=None, models=mods, device=local, fft_precision=args.fft)
 
-    pcm = synth_recording(torch, args.hours, dev, rank)                 # resident in HBM
+    from inaspeechsegmenter_b200.shard import ShardPlan, segment_signal_sharded
+    total = int(args.hours * world * 3600 * SR)            # ONE recording of world x hours, time-sharded
+    plan = ShardPlan(total, world)
+    sa, sb = plan.sample_range(rank)
+    pcm = synth_range(torch, sa, sb, dev)                               # this rank's samples (+halo), resident in HBM
     host = torch.empty(pcm.shape, dtype=torch.int16, pin_memory=True)    # pinned copy for the e2e leg
     host.copy_(pcm)
     torch.cuda.synchronize()
-    audio_h = pcm.numel() / SR / 3600.0
+    audio_h = total / SR / 3600.0 / world                             # per-rank share of the recording
 
     def barrier():
         torch.cuda.synchronize()
@@ -239,8 +250,12 @@ def run_b200(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item(), out
 
-    step_dev = lambda: seg.segment_signal(pcm)          # noqa: E731  inputs already in HBM
-    step_e2e = lambda: seg.segment_signal(host)         # noqa: E731  pinned host -> device inside the call
+    if world == 1:
+        step_dev = lambda: seg.segment_signal(pcm)          # noqa: E731  inputs already in HBM
+        step_e2e = lambda: seg.segment_signal(host)         # noqa: E731  pinned host -> device inside the call
+    else:
+        step_dev = lambda: segment_signal_sharded(seg, pcm, total)[0]     # noqa: E731
+        step_e2e = lambda: segment_signal_sharded(seg, host, total)[0]    # noqa: E731
 
     for _ in range(max(args.warmup, 3)):
         segs = step_dev()
@@ -291,7 +306,9 @@ def run_b200(args):
         'config': {'workload': 'smn+gender on %g h synthetic 16 kHz mono int16 per GPU (BASELINE configs[1])' % args.hours,
                    'networks': 'synthetic-weight stand-ins of the ~1.4M-parameter CNN family (release .hdf5 absent)',
                    'fft': args.fft, 'l2': 'inputs larger than L2 (%.2f GB PCM per step)' % (pcm.numel() * 2 / 1e9),
-                   'parallelism': 'independent recordings per GPU, no data-path collective', 'segments': len(segs),
+                   'parallelism': ('single GPU' if world == 1 else
+                                   'one %g h recording time-sharded over %d GPUs (34-frame halo); NCCL all-gather of loge and CNN posteriors, Viterbi replicated' % (args.hours * world, world)),
+                   'segments': len(segs),
                    'vad_flops_per_patch': seg.vad.nn.flops_per_patch, 'gender_flops_per_patch': seg.gender.nn.flops_per_patch},
         'clocks': clk,
         'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': int(pcm.numel() * 2), 'd2h_bytes_per_step': d2h,
@@ -299,7 +316,7 @@ def run_b200(args):
         'gpu_launches': int(launches),
         'roofline': roof,
     }
-    if not args.no_cpu_baseline and world >= 1:
+    if not args.no_cpu_baseline and world == 1:
         cores = host_cores()
         sample = cpu_sample(args)
         cpu_reference_pass(sample[:SR * 5], mods, cores)

@@ -253,7 +253,59 @@ loge_stats_finalize_kernel(const double *__restrict__ partials, int64_t ntiles, 
     if (threadIdx.x == 0) { stats[0] = ss[0]; stats[1] = sc[0]; }
 }
 
+// Same arithmetic as the fused per-tile partials above: warp w of a tile sums the
+// frames w, w+8, ... in order, the tile sums its 8 warps in order.
+__global__ void __launch_bounds__(128)
+loge_tile_partials_kernel(const float *__restrict__ loge, int64_t L, int64_t ntiles, double *__restrict__ partials)
+{
+    const int64_t tile = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= ntiles) return;
+    const int64_t f0 = tile * FR;
+    const int nfr = (int)min((int64_t)FR, L - f0);
+    double s = 0.0, c = 0.0;
+    for (int w = 0; w < NWARP; ++w) {
+        double sw = 0.0, cw = 0.0;
+        for (int fl = w; fl < nfr; fl += NWARP) {
+            const float le = loge[f0 + fl];
+            if (isfinite(le)) { sw += (double)le; cw += 1.0; }
+        }
+        s += sw; c += cw;
+    }
+    partials[2 * tile] = s;
+    partials[2 * tile + 1] = c;
+}
+
 }  // namespace
+
+static int ensure_partials(iss_ctx *ctx, int64_t ntiles)
+{
+    if (ntiles > ctx->partials_cap) {
+        if (ctx->d_partials) ISS_CUDA_OK(cudaFree(ctx->d_partials));
+        ctx->d_partials = nullptr; ctx->partials_cap = 0;
+        const int64_t cap = ntiles + ntiles / 2 + 1024;
+        cudaError_t e = cudaMalloc(&ctx->d_partials, (size_t)cap * 2 * sizeof(double));
+        if (e != cudaSuccess) { iss_set_error("cudaMalloc partials: %s", cudaGetErrorString(e)); return ISS_ERR_NOMEM; }
+        ctx->partials_cap = cap;
+    }
+    return ISS_OK;
+}
+
+extern "C" int iss_loge_stats(iss_ctx *ctx, const float *d_loge, int64_t L, double *d_loge_stats, void *stream)
+{
+    ISS_REQUIRE(ctx && d_loge_stats, ISS_ERR_INVALID, "iss_loge_stats: NULL argument");
+    ISS_CUDA_OK(cudaSetDevice(ctx->device));
+    cudaStream_t st = iss_stream(stream);
+    if (L <= 0) { ISS_CUDA_OK(cudaMemsetAsync(d_loge_stats, 0, 2 * sizeof(double), st)); return ISS_OK; }
+    ISS_REQUIRE(d_loge, ISS_ERR_INVALID, "iss_loge_stats: NULL buffer");
+    const int64_t ntiles = (L + FR - 1) / FR;
+    int rc = ensure_partials(ctx, ntiles);
+    if (rc != ISS_OK) return rc;
+    loge_tile_partials_kernel<<<(unsigned)((ntiles + 127) / 128), 128, 0, st>>>(d_loge, L, ntiles, ctx->d_partials);
+    loge_stats_finalize_kernel<<<1, 1024, 0, st>>>(ctx->d_partials, ntiles, d_loge_stats);
+    ISS_CUDA_OK(cudaGetLastError());
+    iss_count_launch(2);
+    return ISS_OK;
+}
 
 extern "C" int64_t iss_sidekit_num_frames(int64_t n_samples)
 {
@@ -338,13 +390,9 @@ extern "C" int iss_sidekit_features(iss_ctx *ctx, const void *d_pcm, int pcm_for
     ISS_REQUIRE(d_pcm && d_mspec && d_loge, ISS_ERR_INVALID, "iss_sidekit_features: NULL buffer");
     const int64_t ntiles = (L + FR - 1) / FR;
     ISS_REQUIRE(ntiles < (1ll << 31), ISS_ERR_INVALID, "iss_sidekit_features: signal too long for one call");
-    if (ntiles > ctx->partials_cap) {
-        if (ctx->d_partials) ISS_CUDA_OK(cudaFree(ctx->d_partials));
-        ctx->d_partials = nullptr; ctx->partials_cap = 0;
-        const int64_t cap = ntiles + ntiles / 2 + 1024;
-        cudaError_t e = cudaMalloc(&ctx->d_partials, (size_t)cap * 2 * sizeof(double));
-        if (e != cudaSuccess) { iss_set_error("cudaMalloc partials: %s", cudaGetErrorString(e)); return ISS_ERR_NOMEM; }
-        ctx->partials_cap = cap;
+    {
+        const int prc = ensure_partials(ctx, ntiles);
+        if (prc != ISS_OK) return prc;
     }
     const int vec_ok = ((reinterpret_cast<uintptr_t>(d_pcm) & 15) == 0) ? 1 : 0;
     int rc;

@@ -123,6 +123,15 @@ def diag_trans_exp(exp, dim):
     return ret
 
 
+def loge_stats(ctx, loge, stream=None):
+    """{sum, count} of the finite entries of a CUDA float32 loge array (segmenter.py:70),
+    bit-identical to the reduction fused into the K1 kernel."""
+    stats = torch.empty((2,), dtype=torch.float64, device=loge.device)
+    _lib.check(_lib.load().iss_loge_stats(ctx.handle, _lib.ptr(loge), loge.numel(), _lib.ptr(stats),
+                                          _stream_ptr(loge.device, stream)), 'iss_loge_stats')
+    return stats
+
+
 _EMIS = np.log(np.array([1 - 1e-10, 1e-10]))          # pred2logemission, viterbi_utils.py:29-34
 
 

@@ -84,6 +84,12 @@ int iss_sidekit_features(iss_ctx *ctx, const void *d_pcm, int pcm_format, int64_
                          int fft_precision, float *d_mspec, float *d_loge,
                          double *d_loge_stats, void *stream);
 
+/* Stand-alone version of the {sum, count} reduction over a float32 loge array
+ * (e.g. the all-gathered loge of a time-sharded recording): same summation
+ * order as the fused reduction inside iss_sidekit_features, hence bit-identical
+ * d_loge_stats for the same loge values. */
+int iss_loge_stats(iss_ctx *ctx, const float *d_loge, int64_t L, double *d_loge_stats, void *stream);
+
 /* ---- K3: Viterbi smoothing ------------------------------------------------
  * Replaces viterbi_decoding(emission, transition) for the two ways the hot
  * path calls it (inaSpeechSegmenter/pyannote_viterbi.py:118-224; callers
