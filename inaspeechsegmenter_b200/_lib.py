@@ -57,6 +57,16 @@ SIGNATURES = {
     'iss_cnn_flops_per_patch': (_d, [_vp]),
     'iss_cnn_workspace_bytes': (_i64, [_vp, _i64, _i]),
     'iss_cnn_forward': (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i64, _vp]),
+    'iss_vbx_num_frames': (_i64, [_i64]),
+    'iss_vbx_upload_tables': (_i, [_vp, _vp, _vp]),
+    'iss_vbx_work_bytes': (_i64, [_i64]),
+    'iss_vbx_features': (_i, [_vp, _vp, _i, _i64, _vp, _vp, _vp, _vp]),
+    'iss_resnet_blob_len': (_i64, [_i, _i, _i, _vp]),
+    'iss_resnet_create': (_i, [_vp, _vp, _i64, _i, _i, _i, _vp, _c.POINTER(_vp)]),
+    'iss_resnet_destroy': (_i, [_vp]),
+    'iss_resnet_flops_per_window': (_d, [_vp, _i]),
+    'iss_resnet_workspace_bytes': (_i64, [_vp, _i, _i]),
+    'iss_resnet_embed': (_i, [_vp, _vp, _vp, _i64, _vp, _i, _i, _vp, _vp, _i64, _vp]),
     'iss_cnn_profile': (_i, [_vp, _i]),
     'iss_cnn_profile_read': (_i, [_vp, _c.POINTER(_d), _c.POINTER(_i64), _c.POINTER(_d)]),
     'iss_cnn_layer_flops': (_d, [_vp, _i]),

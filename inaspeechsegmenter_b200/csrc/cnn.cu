@@ -18,7 +18,7 @@
 #include <string.h>
 #include <vector>
 
-#include "iss_common.cuh"
+#include "conv_gemm.cuh"
 
 namespace {
 
@@ -103,188 +103,6 @@ patch_stats_kernel(const float *__restrict__ mspec, int ld, int w, int64_t n, Pa
     }
 }
 
-// ------------------------------------------------------------------ implicit-GEMM conv / dense (fp32 CUDA cores)
-struct ConvArgs {
-    const float *in;        // NHWC activations, or the log-mel rows when FIRST
-    const float *w;         // [K][N]
-    const float *bias, *pre_scale, *pre_shift, *post_scale, *post_shift;
-    float *out;             // [M][N]
-    int64_t M;              // n_img * OH * OW
-    int N, K;
-    int H, W, C;            // input dims
-    int OH, OW;
-    int KH, KW, SH, SW, PT, PL;
-    int flags;
-    // FIRST only
-    int ld;
-    const int32_t *row0; const float *mu; const float *sigma;
-};
-
-constexpr int BM = 128, BK = 16;
-
-template <int BN, bool FIRST>
-__global__ void __launch_bounds__(256, 2)
-conv_gemm_f32_kernel(const ConvArgs a)
-{
-    constexpr int TM = 8, TN = BN / 16;
-    __shared__ __align__(16) float As[2][BK][BM];
-    __shared__ __align__(16) float Bs[2][BK][BN];
-    const int tid = threadIdx.x;
-    const int tx = tid & 15, ty = tid >> 4;
-    const int64_t m0 = (int64_t)blockIdx.x * BM;
-    const int n0 = blockIdx.y * BN;
-
-    // ---- per-thread A-gather coordinates: one output position, 8 consecutive k per tile ----
-    const int ml = tid & (BM - 1), kh2 = tid >> 7;
-    const int64_t m = m0 + ml;
-    const bool m_ok = m < a.M;
-    int ih0 = 0, iw0 = 0;
-    const float *in_img = a.in;
-    float mu = 0.f, sg = 1.f;
-    {
-        const int64_t mm = m_ok ? m : 0;
-        const int ohw = a.OH * a.OW;
-        const int64_t img = mm / ohw;
-        const int rem = (int)(mm - img * ohw);
-        const int oh = rem / a.OW, ow = rem - oh * a.OW;
-        ih0 = oh * a.SH - a.PT; iw0 = ow * a.SW - a.PL;
-        if (FIRST) { in_img = a.in + (int64_t)a.row0[img] * a.ld; mu = a.mu[img]; sg = a.sigma[img]; }
-        else in_img = a.in + img * ((int64_t)a.H * a.W * a.C);
-    }
-    const bool vecA = !FIRST && (a.C % 8 == 0);
-    const bool vecB = (a.N % 4 == 0);
-
-    float ra[8];
-    float rb[TN];
-
-    auto load_tiles = [&](int kt) {
-        const int kb = kt * BK + kh2 * 8;
-        if (vecA) {
-            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-            if (m_ok && kb < a.K) {
-                const int tap = kb / a.C, c = kb - tap * a.C;
-                const int r = tap / a.KW, s = tap - r * a.KW;
-                const int ih = ih0 + r, iw = iw0 + s;
-                if (ih >= 0 && ih < a.H && iw >= 0 && iw < a.W) {
-                    const float4 *p = reinterpret_cast<const float4 *>(in_img + ((int64_t)ih * a.W + iw) * a.C + c);
-                    v0 = __ldg(p); v1 = __ldg(p + 1);
-                }
-            }
-            ra[0] = v0.x; ra[1] = v0.y; ra[2] = v0.z; ra[3] = v0.w;
-            ra[4] = v1.x; ra[5] = v1.y; ra[6] = v1.z; ra[7] = v1.w;
-        } else {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int k = kb + q;
-                float v = 0.f;
-                if (m_ok && k < a.K) {
-                    const int tap = k / a.C, c = k - tap * a.C;
-                    const int r = tap / a.KW, s = tap - r * a.KW;
-                    const int ih = ih0 + r, iw = iw0 + s;
-                    if (ih >= 0 && ih < a.H && iw >= 0 && iw < a.W) {
-                        if (FIRST) v = __fdiv_rn(__fsub_rn(__ldg(in_img + (int64_t)ih * a.ld + iw), mu), sg);
-                        else v = __ldg(in_img + ((int64_t)ih * a.W + iw) * a.C + c);
-                    }
-                }
-                ra[q] = v;
-            }
-        }
-        // B tile: BK x BN floats, 256 threads * TN
-        {
-            const int e = tid * TN;                  // element index in the tile
-            const int kk = e / BN, nn = e - kk * BN;
-            const int k = kt * BK + kk, n = n0 + nn;
-            if (vecB && k < a.K && n + TN <= a.N) {
-#pragma unroll
-                for (int q = 0; q < TN; q += 4) {
-                    const float4 v = __ldg(reinterpret_cast<const float4 *>(a.w + (int64_t)k * a.N + n + q));
-                    rb[q] = v.x; rb[q + 1] = v.y; rb[q + 2] = v.z; rb[q + 3] = v.w;
-                }
-            } else {
-#pragma unroll
-                for (int q = 0; q < TN; ++q) rb[q] = (k < a.K && n + q < a.N) ? __ldg(a.w + (int64_t)k * a.N + n + q) : 0.f;
-            }
-        }
-    };
-    auto store_tiles = [&](int buf) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) As[buf][kh2 * 8 + q][ml] = ra[q];
-        const int e = tid * TN;
-        const int kk = e / BN, nn = e - kk * BN;
-#pragma unroll
-        for (int q = 0; q < TN; ++q) Bs[buf][kk][nn + q] = rb[q];
-    };
-
-    float acc[TM][TN];
-#pragma unroll
-    for (int i = 0; i < TM; ++i)
-#pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
-
-    const int nkt = (a.K + BK - 1) / BK;
-    load_tiles(0);
-    store_tiles(0);
-    __syncthreads();
-    for (int kt = 0; kt < nkt; ++kt) {
-        const int buf = kt & 1;
-        if (kt + 1 < nkt) load_tiles(kt + 1);
-#pragma unroll
-        for (int kk = 0; kk < BK; ++kk) {
-            float av[TM], bv[TN];
-            const float4 a0 = *reinterpret_cast<const float4 *>(&As[buf][kk][ty * TM]);
-            const float4 a1 = *reinterpret_cast<const float4 *>(&As[buf][kk][ty * TM + 4]);
-            av[0] = a0.x; av[1] = a0.y; av[2] = a0.z; av[3] = a0.w; av[4] = a1.x; av[5] = a1.y; av[6] = a1.z; av[7] = a1.w;
-#pragma unroll
-            for (int q = 0; q < TN; q += 4) {
-                const float4 b = *reinterpret_cast<const float4 *>(&Bs[buf][kk][tx * TN + q]);
-                bv[q] = b.x; bv[q + 1] = b.y; bv[q + 2] = b.z; bv[q + 3] = b.w;
-            }
-#pragma unroll
-            for (int i = 0; i < TM; ++i)
-#pragma unroll
-                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-        }
-        if (kt + 1 < nkt) store_tiles(buf ^ 1);
-        __syncthreads();
-    }
-
-    // ---- epilogue: bias -> affine(pre) -> relu -> affine(post) ----
-    float eb[TN], es1[TN], et1[TN], es2[TN], et2[TN];
-#pragma unroll
-    for (int j = 0; j < TN; ++j) {
-        const int n = n0 + tx * TN + j;
-        const bool ok = n < a.N;
-        eb[j] = (ok && (a.flags & ISS_F_BIAS)) ? a.bias[n] : 0.f;
-        es1[j] = (ok && (a.flags & ISS_F_AFFINE_PRE)) ? a.pre_scale[n] : 1.f;
-        et1[j] = (ok && (a.flags & ISS_F_AFFINE_PRE)) ? a.pre_shift[n] : 0.f;
-        es2[j] = (ok && (a.flags & ISS_F_AFFINE_POST)) ? a.post_scale[n] : 1.f;
-        et2[j] = (ok && (a.flags & ISS_F_AFFINE_POST)) ? a.post_shift[n] : 0.f;
-    }
-#pragma unroll
-    for (int i = 0; i < TM; ++i) {
-        const int64_t mr = m0 + ty * TM + i;
-        if (mr >= a.M) continue;
-        float v[TN];
-#pragma unroll
-        for (int j = 0; j < TN; ++j) {
-            float x = acc[i][j] + eb[j];
-            if (a.flags & ISS_F_AFFINE_PRE) x = fmaf(x, es1[j], et1[j]);
-            if (a.flags & ISS_F_RELU) x = fmaxf(x, 0.f);
-            if (a.flags & ISS_F_SIGMOID) x = 1.f / (1.f + expf(-x));
-            if (a.flags & ISS_F_AFFINE_POST) x = fmaf(x, es2[j], et2[j]);
-            v[j] = x;
-        }
-        float *o = a.out + mr * a.N + n0 + tx * TN;
-        if (vecB && n0 + tx * TN + TN <= a.N) {
-#pragma unroll
-            for (int q = 0; q < TN; q += 4) *reinterpret_cast<float4 *>(o + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
-        } else {
-#pragma unroll
-            for (int j = 0; j < TN; ++j) if (n0 + tx * TN + j < a.N) o[j] = v[j];
-        }
-    }
-}
-
 // ------------------------------------------------------------------ max pooling (NHWC)
 __global__ void __launch_bounds__(256)
 maxpool_nhwc_kernel(const float *__restrict__ in, float *__restrict__ out, int64_t total, int H, int W, int C,
@@ -334,22 +152,6 @@ softmax_head_kernel(const float *__restrict__ logits, const uint8_t *__restrict_
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-
-template <bool FIRST>
-int launch_conv(const ConvArgs &a, cudaStream_t st)
-{
-    const int64_t gm = (a.M + BM - 1) / BM;
-    ISS_REQUIRE(gm < (1ll << 31), ISS_ERR_INVALID, "conv: M too large");
-    if (a.N <= 64) {
-        dim3 grid((unsigned)gm, (unsigned)((a.N + 63) / 64));
-        conv_gemm_f32_kernel<64, FIRST><<<grid, 256, 0, st>>>(a);
-    } else {
-        dim3 grid((unsigned)gm, (unsigned)((a.N + 127) / 128));
-        conv_gemm_f32_kernel<128, FIRST><<<grid, 256, 0, st>>>(a);
-    }
-    ISS_CUDA_OK(cudaGetLastError());
-    return ISS_OK;
-}
 
 }  // namespace
 
@@ -525,6 +327,7 @@ extern "C" int iss_cnn_forward(iss_ctx *ctx, iss_cnn *cnn, const float *d_mspec,
                 maxpool_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(cur, dst, total, Lr.in_h, Lr.in_w, Lr.in_c,
                     Lr.out_h, Lr.out_w, d.kh, d.kw, d.sh, d.sw, d.pad_top, d.pad_left);
                 ISS_CUDA_OK(cudaGetLastError());
+                iss_count_launch();
             } else {
                 ConvArgs a = {};
                 a.w = blob + d.w_off;
@@ -548,14 +351,13 @@ extern "C" int iss_cnn_forward(iss_ctx *ctx, iss_cnn *cnn, const float *d_mspec,
                 if (li == 0) {
                     ISS_REQUIRE(d.kind == ISS_LAYER_CONV2D, ISS_ERR_UNSUPPORTED, "iss_cnn_forward: first layer must be Conv2D");
                     a.in = d_mspec; a.ld = ld; a.row0 = pa.row0 + b0; a.mu = pa.mu + b0; a.sigma = pa.sigma + b0;
-                    rc = launch_conv<true>(a, st);
+                    rc = iss_launch_conv(a, true, st);
                 } else {
                     a.in = cur;
-                    rc = launch_conv<false>(a, st);
+                    rc = iss_launch_conv(a, false, st);
                 }
                 if (rc != ISS_OK) return rc;
             }
-            iss_count_launch();
             if (prof) {
                 ISS_CUDA_OK(cudaEventRecord(cnn->prof_ev[cnn->prof_used + 1], st));
                 cnn->prof_used += 2;

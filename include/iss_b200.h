@@ -176,6 +176,44 @@ int iss_cnn_forward(iss_ctx *ctx, iss_cnn *cnn, const float *d_mspec, int64_t L,
                     const int32_t *h_seg_start, const int32_t *h_seg_stop, int n_seg,
                     float *d_probs, void *d_work, int64_t work_bytes, void *stream);
 
+/* ---- K4: VBx / HTK 64-band log-mel front-end + floating CMVN ----------------
+ * Replaces get_features(signal) (inaSpeechSegmenter/vbx_segmenter.py:72-89 on top
+ * of features_vbx.py:62-148): trunc(signal*2^15) + dither, mirror pad 120/200,
+ * frames 400/160, per-frame mean removal + pre-emphasis, Povey window, 512-point
+ * power spectrum, log(max(1, . fbank)), cmvn_floating_kaldi(150, 149), float32. */
+
+/* M = (n + 320 - 400) / 160 + 1 feature frames (0 if n < 200). */
+int64_t iss_vbx_num_frames(int64_t n_samples);
+/* h_fbank = mel_fbank_mx(400, 16000, NUMCHANS=64, LOFREQ=20, HIFREQ=7600,
+ * htk_bug=False) (float64 [257][64]); h_window = povey_window(400) (float64). */
+int iss_vbx_upload_tables(iss_ctx *ctx, const double *h_fbank, const double *h_window);
+int64_t iss_vbx_work_bytes(int64_t n_samples);
+/* d_dither: float64 [n] = 8*(2u-1), u the np.random.seed(3); np.random.rand(n)
+ * stream (a prefix of one fixed MT19937 sequence -- keep it resident), or NULL for
+ * no dither.  d_fea: float32 [M][64].  d_work: iss_vbx_work_bytes(n) of scratch. */
+int iss_vbx_features(iss_ctx *ctx, const void *d_pcm, int pcm_format, int64_t n_samples,
+                     const double *d_dither, float *d_fea, void *d_work, void *stream);
+
+/* ---- K5: ResNet101 x-vector extractor ----------------------------------------
+ * Replaces VBxExtractor.get_embedding / OnnxBackendExtractor (vbx_segmenter.py:
+ * 249-266) == ResNet.forward (resnet.py:115-130), batched over the windows of
+ * VBxExtractor.__call__ (vbx_segmenter.py:217-246).
+ * Blob layout (float32), in module order conv1, layer1.0 ... layer4.2, each
+ * Bottleneck as conv1, conv2, conv3[, shortcut]; every convolution contributes
+ * kernel [kh][kw][cin][cout], then BatchNorm folded to scale[cout], shift[cout];
+ * finally embedding weight transposed [2*C*H][embed] and bias [embed]. */
+int64_t iss_resnet_blob_len(int m_channels, int feat_dim, int embed_dim, const int *num_blocks);
+int iss_resnet_create(iss_ctx *ctx, const float *h_blob, int64_t blob_len, int m_channels, int feat_dim,
+                      int embed_dim, const int *num_blocks, iss_resnet **out);
+int iss_resnet_destroy(iss_resnet *net);
+double iss_resnet_flops_per_window(const iss_resnet *net, int win_len);
+int64_t iss_resnet_workspace_bytes(const iss_resnet *net, int n_windows, int win_len);
+/* d_fea: float32 [M][feat_dim] (CMVN'd features); window i = rows
+ * [h_win_start[i], h_win_start[i] + win_len); d_emb: float32 [n_windows][embed]. */
+int iss_resnet_embed(iss_ctx *ctx, iss_resnet *net, const float *d_fea, int64_t M,
+                     const int32_t *h_win_start, int n_windows, int win_len, float *d_emb,
+                     void *d_work, int64_t work_bytes, void *stream);
+
 /* Live roofline support: record CUDA events around every launch of layer
  * `layer` (index into the iss_layer_desc list; -1 switches profiling off) on
  * the stream the launch uses.  iss_cnn_profile_read synchronises those events,

@@ -148,6 +148,35 @@ def main():
             out['vbx_%s_M' % name] = np.int64(M)
             print('vbx %-10s M=%d identical to reference' % (name, M))
 
+    # ---- ResNet101 architecture restatement vs the real resnet.py --------------
+    if vx is not None:
+        import torch
+        ref_resnet = load_ref('resnet')
+        sd = vx.synthetic_resnet101_state(seed=5)
+        net = ref_resnet.ResNet101(feat_dim=64, embed_dim=256)
+        missing, unexpected = net.load_state_dict(sd, strict=False)
+        assert not unexpected and all(k.endswith('num_batches_tracked') for k in missing), (missing, unexpected)
+        net.eval()
+        g = torch.Generator().manual_seed(9)
+        x = torch.randn(2, 64, 144, generator=g)
+        xs = torch.randn(1, 64, 131, generator=g)                 # a tail-window length
+        with torch.no_grad():
+            y_ref, ys_ref = net(x.clone()), net(xs.clone())
+        orc = vx.ResNet101Oracle(sd)
+        y, ys = orc.forward(x), orc.forward(xs)
+        assert torch.equal(y, y_ref) and torch.equal(ys, ys_ref), (float((y - y_ref).abs().max()))
+        out['resnet_x'], out['resnet_y'] = x.numpy(), y_ref.numpy()
+        out['resnet_xs'], out['resnet_ys'] = xs.numpy(), ys_ref.numpy()
+        print('resnet101: functional restatement identical to resnet.py (|y| mean %.3f)' % float(y_ref.abs().mean()))
+        # window plan vs the reference loop (vbx_segmenter.py:222-243 re-typed as a generator of (start, stop))
+        for M in (9, 10, 33, 34, 143, 144, 145, 167, 168, 169, 200, 1464, 1465):
+            ref_plan, start = [], 0
+            for start in range(0, M - 144, 24):
+                ref_plan.append((start, start + 144))
+            if M - start - 24 >= 10:
+                ref_plan.append((start + 24, M))
+            assert [(a, a + n) for a, n, _ in vx.window_plan(M)] == ref_plan, M
+
     np.savez_compressed(os.path.join(HERE, 'reference_golden.npz'), **out)
     print('wrote', os.path.join(HERE, 'reference_golden.npz'))
 

@@ -1,0 +1,123 @@
+"""VBx x-vector path: CPU host-logic tests + GPU parity tests (K4 features, K5 ResNet101)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip('torch')
+
+
+# ------------------------------------------------------------------ CPU
+def test_vbx_oracle_features_golden(golden, media):
+    """oracle restatement == real features_vbx.py (goldens made by make_golden.py)."""
+    import hashlib
+    from oracle import segmenter_oracle as so, vbx_oracle as vx
+    sig = so.read_wav_16k_mono(os.path.join(media, 'lamartine.wav'), dtype='float64')
+    cases = {'lamartine': sig, 'synth': golden['synth_sig'].astype(np.float64),
+             'short': golden['synth_sig'][:16000 * 2 + 77].astype(np.float64)}
+    for name, s in cases.items():
+        fea = vx.get_features(s)
+        assert len(fea) == int(golden['vbx_%s_M' % name])
+        assert np.array_equal(fea[golden['vbx_%s_rows' % name]], golden['vbx_%s_fea' % name])
+        assert hashlib.sha256(np.ascontiguousarray(fea).tobytes()).hexdigest() == str(golden['vbx_%s_sha' % name])
+
+
+def test_vbx_host_tables_and_plan():
+    from inaspeechsegmenter_b200 import vbx_segmenter as vb
+    from oracle import vbx_oracle as vx
+    assert np.array_equal(vb.mel_fbank_htk64(), vx.mel_bank()) and np.count_nonzero(vx.mel_bank()) == 475
+    assert np.array_equal(vb.povey_window(), vx.povey_window())
+    d = vb.DitherCache('cpu').get(1000).numpy()[:1000]
+    assert np.array_equal(d, vx.dither_stream(1000))
+    for M in (5, 9, 10, 33, 34, 35, 143, 144, 145, 167, 168, 169, 170, 200, 1464):
+        assert vb.window_plan(M) == vx.window_plan(M)
+
+
+def test_resnet_oracle_golden(golden):
+    """functional ResNet101 restatement == real resnet.py output stored in the golden file."""
+    from oracle import vbx_oracle as vx
+    net = vx.ResNet101Oracle(vx.synthetic_resnet101_state(seed=5), threads=4)
+    y = net.forward(torch.from_numpy(golden['resnet_x'][:1]))
+    assert np.allclose(y.numpy(), golden['resnet_y'][:1], rtol=0, atol=1e-4 * np.abs(golden['resnet_y']).max())
+
+
+def test_resnet_blob_layout():
+    from inaspeechsegmenter_b200 import _lib, vbx_segmenter as vb
+    from oracle import vbx_oracle as vx
+    sd = vx.synthetic_resnet101_state(seed=5)
+    blob = vb.resnet_blob_from_state(sd)
+    nb = (ctypes.c_int * 4)(*vb.NUM_BLOCKS)
+    need = _lib.load().iss_resnet_blob_len(32, 64, 256, ctypes.cast(nb, ctypes.c_void_p))
+    assert blob.size == need
+    nparam = sum(v.numel() for k, v in sd.items() if 'running' not in k)
+    assert abs(nparam - 14.84e6) < 0.05e6            # 14.84 M parameters
+
+
+# ------------------------------------------------------------------ GPU
+gpu = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def vctx():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from inaspeechsegmenter_b200 import engine
+    return engine.Context(0)
+
+
+@gpu
+def test_k4_features_vs_reference_golden(vctx, golden, media):
+    from inaspeechsegmenter_b200 import vbx_segmenter as vb
+    from oracle import segmenter_oracle as so, vbx_oracle as vx
+    fe = vb.VbxFrontEnd(vctx)
+    sig = so.read_wav_16k_mono(os.path.join(media, 'lamartine.wav'), dtype='float32')
+    cases = {'lamartine': sig, 'synth': golden['synth_sig'], 'short': golden['synth_sig'][:16000 * 2 + 77]}
+    for name, s in cases.items():
+        ref = vx.get_features(s.astype(np.float64))
+        got = fe(torch.from_numpy(np.ascontiguousarray(s, dtype=np.float32)).cuda()).cpu().numpy()
+        assert got.shape == ref.shape == (int(golden['vbx_%s_M' % name]), 64)
+        err = np.abs(got - ref).max()
+        exact = float((got == ref).mean())
+        assert err <= 2e-6, (name, err)                 # float64 pipeline, float32 output: <= 1-2 ulp
+        assert exact > 0.98, (name, exact)
+        assert np.abs(got[golden['vbx_%s_rows' % name]] - golden['vbx_%s_fea' % name]).max() <= 2e-6
+    # int16 PCM input == the same samples as float
+    s16 = np.round(golden['synth_sig'] * 32768).astype(np.int16)
+    a = fe(torch.from_numpy(s16).cuda())
+    b = fe(torch.from_numpy(golden['synth_sig']).cuda())
+    assert torch.equal(a, b)
+    # the public helper
+    assert np.abs(vb.get_features(golden['synth_sig'].astype(np.float64)) - vx.get_features(golden['synth_sig'].astype(np.float64))).max() <= 2e-6
+
+
+@gpu
+def test_k5_resnet_vs_oracle(vctx, golden):
+    from inaspeechsegmenter_b200 import vbx_segmenter as vb
+    from oracle import vbx_oracle as vx
+    sd = vx.synthetic_resnet101_state(seed=5)
+    ext = vb.B200BackendExtractor(state_dict=sd, ctx=vctx)
+    assert abs(ext.flops_per_window - 11.30e9) < 0.05e9       # 5.65 GMAC per 64x144 window
+    x, y = golden['resnet_x'], golden['resnet_y']              # produced by the REAL resnet.py
+    scale = np.abs(y).max()
+    for i in range(len(x)):
+        got = ext.get_embedding(x[i].T)                        # get_embedding takes [T, 64]
+        assert np.abs(got - y[i]).max() <= 2e-4 * scale, np.abs(got - y[i]).max() / scale
+    got = ext.get_embedding(golden['resnet_xs'][0].T)          # tail-window length 131
+    assert np.abs(got - golden['resnet_ys'][0]).max() <= 2e-4 * np.abs(golden['resnet_ys']).max()
+
+
+@gpu
+def test_vbx_extractor_call_vs_oracle(vctx, golden):
+    """B200BackendExtractor.__call__ (batched) == the reference windowing loop with the oracle network."""
+    from inaspeechsegmenter_b200 import vbx_segmenter as vb
+    from oracle import vbx_oracle as vx
+    sd = vx.synthetic_resnet101_state(seed=5)
+    ext = vb.B200BackendExtractor(state_dict=sd, ctx=vctx)
+    fea = vx.get_features(golden['synth_sig'].astype(np.float64))[:330]     # 8 regular windows + a tail
+    ref = vx.extract_xvectors(fea, vx.ResNet101Oracle(sd), 'clip', 3.3)
+    got = ext('clip', fea, 3.3)
+    assert [(k, s) for k, s, _ in got] == [(k, s) for k, s, _ in ref]
+    scale = max(np.abs(x).max() for _, _, x in ref)
+    for (_, _, a), (_, _, b) in zip(got, ref):
+        assert np.abs(a - b).max() <= 2e-4 * scale
