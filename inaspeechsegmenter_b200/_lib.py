@@ -35,6 +35,7 @@ LAYER_CONV2D, LAYER_DENSE, LAYER_MAXPOOL = 1, 2, 3
 F_BIAS, F_AFFINE_PRE, F_RELU, F_AFFINE_POST, F_SOFTMAX, F_SIGMOID = 1, 2, 4, 8, 16, 32
 PCM_F32, PCM_S16 = 0, 1
 FFT_FP32, FFT_FP64 = 0, 1
+GEMM_FP32, GEMM_TC_SS, GEMM_TC_TS = 0, 1, 2
 
 # name -> (restype, argtypes); must list every symbol include/iss_b200.h declares
 _vp, _i, _i64, _d = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_double
@@ -44,6 +45,8 @@ SIGNATURES = {
     'iss_ctx_create': (_i, [_i, _c.POINTER(_vp)]),
     'iss_ctx_destroy': (_i, [_vp]),
     'iss_launch_count': (_i64, []),
+    'iss_set_gemm_mode': (_i, [_i]),
+    'iss_get_gemm_mode': (_i, []),
     'iss_sidekit_num_frames': (_i64, [_i64]),
     'iss_sidekit_upload_tables': (_i, [_vp, _vp, _vp]),
     'iss_sidekit_features': (_i, [_vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _vp]),

@@ -31,6 +31,8 @@ struct Layer {
     iss_layer_desc d;
     int in_h, in_w, in_c;
     int out_h, out_w, out_c;
+    float *d_wt = nullptr;      // tensor-core weights [2][N][Kp] (eligible layers only)
+    int Kp = 0;
 };
 
 }  // namespace
@@ -155,6 +157,8 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
 
+extern "C" int iss_cnn_destroy(iss_cnn *cnn);
+
 extern "C" int iss_cnn_create(iss_ctx *ctx, const iss_layer_desc *layers, int n_layers,
                               const float *h_blob, int64_t blob_len, int in_h, int in_w, iss_cnn **out)
 {
@@ -219,6 +223,16 @@ extern "C" int iss_cnn_create(iss_ctx *ctx, const iss_layer_desc *layers, int n_
     if (e != cudaSuccess) { delete m; iss_set_error("cudaMalloc blob: %s", cudaGetErrorString(e)); return ISS_ERR_NOMEM; }
     e = cudaMemcpy(m->d_blob, h_blob, (size_t)blob_len * sizeof(float), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaFree(m->d_blob); delete m; iss_set_error("cudaMemcpy blob: %s", cudaGetErrorString(e)); return ISS_ERR_CUDA; }
+    for (size_t i = 1; i < m->layers.size(); ++i) {          // layer 0 gathers from the log-mel rows (fp32 kernel)
+        Layer &L = m->layers[i];
+        const iss_layer_desc &d = L.d;
+        if (d.kind == ISS_LAYER_MAXPOOL) continue;
+        const int K = (d.kind == ISS_LAYER_DENSE) ? d.cin : d.kh * d.kw * d.cin;
+        const int C = (d.kind == ISS_LAYER_DENSE) ? d.cin : d.cin;
+        if (C % 32 != 0 || K % 32 != 0 || d.cout % 32 != 0) continue;
+        int rc = iss_prepare_tc_weights(h_blob + d.w_off, K, d.cout, &L.d_wt, &L.Kp);
+        if (rc != ISS_OK) { iss_cnn_destroy(m); return rc; }
+    }
     *out = m;
     return ISS_OK;
 }
@@ -228,6 +242,7 @@ extern "C" int iss_cnn_destroy(iss_cnn *cnn)
     if (!cnn) return ISS_OK;
     cudaSetDevice(cnn->ctx->device);
     for (cudaEvent_t ev : cnn->prof_ev) cudaEventDestroy(ev);
+    for (Layer &L : cnn->layers) if (L.d_wt) cudaFree(L.d_wt);
     if (cnn->d_blob) cudaFree(cnn->d_blob);
     delete cnn;
     return ISS_OK;
@@ -337,6 +352,7 @@ extern "C" int iss_cnn_forward(iss_ctx *ctx, iss_cnn *cnn, const float *d_mspec,
                 a.post_scale = (d.flags & ISS_F_AFFINE_POST) ? blob + d.post_scale_off : nullptr;
                 a.post_shift = (d.flags & ISS_F_AFFINE_POST) ? blob + d.post_shift_off : nullptr;
                 a.out = dst;
+                if (Lr.d_wt) { a.wt_hi = Lr.d_wt; a.wt_lo = Lr.d_wt + (size_t)d.cout * Lr.Kp; a.Kp = Lr.Kp; }
                 a.flags = d.flags & ~ISS_F_SOFTMAX;
                 a.N = d.cout;
                 if (d.kind == ISS_LAYER_DENSE) {

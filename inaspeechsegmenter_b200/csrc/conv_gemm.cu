@@ -194,5 +194,9 @@ int launch_conv_t(const ConvArgs &a, cudaStream_t st)
 
 int iss_launch_conv(const ConvArgs &a, bool first, cudaStream_t st)
 {
+    if (!first) {
+        const int mode = iss_get_gemm_mode();
+        if (mode != ISS_GEMM_FP32 && iss_conv_tc_eligible(a)) return iss_launch_conv_tc(a, mode, st);
+    }
     return first ? launch_conv_t<true>(a, st) : launch_conv_t<false>(a, st);
 }

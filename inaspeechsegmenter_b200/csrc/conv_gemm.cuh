@@ -20,7 +20,22 @@ struct ConvArgs {
     // `first` (sliding z-normalised patches of the segmenter CNNs) only
     int ld;
     const int32_t *row0; const float *mu; const float *sigma;
+    // tensor-core path: weights transposed + split, [N][Kp] each (nullptr => fp32 CUDA-core kernel)
+    const float *wt_hi; const float *wt_lo; int Kp;
 };
+
+#define ISS_GEMM_FP32  0      /* fp32 CUDA cores (conv_gemm.cu) */
+#define ISS_GEMM_TC_SS 1      /* tcgen05 3xTF32, A and B from shared memory */
+#define ISS_GEMM_TC_TS 2      /* tcgen05 3xTF32, A from tensor memory, B from shared memory */
+#ifndef ISS_GEMM_DEFAULT
+#define ISS_GEMM_DEFAULT ISS_GEMM_FP32
+#endif
+
+extern "C" int iss_get_gemm_mode(void);
+bool iss_conv_tc_eligible(const ConvArgs &a);
+int iss_launch_conv_tc(const ConvArgs &a, int mode, cudaStream_t st);
+// W[K][N] -> device buffer [2][N][Kp] (hi then lo), Kp = K rounded up to 32
+int iss_prepare_tc_weights(const float *h_w, int K, int N, float **d_out, int *Kp_out);
 
 // Launches the layer on `st`.  first = gather from log-mel rows with (x - mu) / sigma.
 int iss_launch_conv(const ConvArgs &a, bool first, cudaStream_t st);

@@ -1,0 +1,411 @@
+// conv_gemm_tc.cu -- implicit-GEMM convolution / dense layer on the 5th-gen tensor
+// cores (tcgen05.mma, accumulators in TMEM) with fp32-class accuracy ("3xTF32").
+//
+// Why 3xTF32: the reference evaluates its CNNs in fp32 (TF-CPU) and the parity bar is
+// 1e-4 on the per-frame softmax; a single TF32 pass (10-bit mantissa) misses it.  Every
+// fp32 operand x is split exactly into hi = x with the 13 low mantissa bits cleared (a
+// valid TF32 number) and lo = x - hi; the product is accumulated as
+//      A.B ~= Ah.Bh + Ah.Bl + Al.Bh          (dropped Al.Bl ~ 2^-22 relative)
+// i.e. three kind::tf32 MMAs per K-step into the same fp32 TMEM accumulator.
+//
+// Tile: 128 output positions (UMMA_M = 128, cta_group::1) x BN output channels, K in
+// blocks of 32 floats (= one 128-byte swizzle row).  Roles per CTA (160 threads):
+//   warps 0-3  producers: thread r owns A row r: im2col gather of 32 contiguous
+//              channels of one filter tap (NHWC => one 128-byte global segment), exact
+//              hi/lo split in registers, then
+//                SS mode: st.shared in the canonical K-major SWIZZLE_128B layout;
+//                TS mode: tcgen05.st straight into TMEM (A never touches shared
+//                         memory, which is the bottleneck resource for narrow-N tiles);
+//              plus the pre-split, pre-transposed weight tile [BN][32] into smem.
+//              After the K loop the same warps run the epilogue: tcgen05.ld of their
+//              32-lane TMEM quadrant, bias -> BN affine -> (+residual) -> ReLU -> affine,
+//              float4 stores.
+//   warp 4     TMEM allocator + single-thread MMA issuer; tcgen05.commit releases the
+//              smem/TMEM stage back to the producers and finally signals the epilogue.
+// Two CTAs fit per SM (<= 113 KB smem, 256 TMEM columns each) so one CTA's epilogue
+// overlaps the other's main loop.
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "conv_gemm.cuh"
+
+namespace {
+
+constexpr int TBM = 128, TBK = 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// K-major, SWIZZLE_128B operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);            // start address (16-byte units)
+    d |= (uint64_t)1 << 16;                                 // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                       // stride byte offset: 8 rows * 128 B
+    d |= (uint64_t)1 << 46;                                 // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                                 // SWIZZLE_128B
+    return d;
+}
+
+__device__ __forceinline__ void umma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr),
+          "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+          "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+          "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+
+constexpr uint32_t tmem_cols_pow2(uint32_t n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
+
+template <int BN, int STAGES, bool A_TMEM>
+struct TcCfg {
+    static constexpr int A_TILE = A_TMEM ? 0 : TBM * TBK * 4;           // bytes per hi (or lo) A tile in smem
+    static constexpr int B_TILE = BN * TBK * 4;
+    static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
+    static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr uint32_t TMEM_USED = BN + (A_TMEM ? STAGES * 2 * TBK : 0);
+    static constexpr uint32_t TMEM_COLS = tmem_cols_pow2(TMEM_USED);
+};
+
+template <int BN, int STAGES, bool A_TMEM>
+__global__ void __launch_bounds__(160)
+conv_gemm_tc_kernel(const ConvArgs a)
+{
+    using Cfg = TcCfg<BN, STAGES, A_TMEM>;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * Cfg::STAGE);
+    uint64_t *full = bars, *empty = bars + STAGES, *accum = bars + 2 * STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t m0 = (int64_t)blockIdx.x * TBM;
+    const int n0 = blockIdx.y * BN;
+    const int nkb = a.Kp / TBK;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
+        mbar_init(accum, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // ============================ producers ============================
+        const int r = tid;                                   // A row in the tile == TMEM lane
+        const int64_t m = m0 + r;
+        const bool m_ok = m < a.M;
+        int ih0 = 0, iw0 = 0;
+        const float *in_img = a.in;
+        {
+            const int64_t mm = m_ok ? m : 0;
+            const int ohw = a.OH * a.OW;
+            const int64_t img = mm / ohw;
+            const int rem = (int)(mm - img * ohw);
+            const int oh = rem / a.OW, ow = rem - oh * a.OW;
+            ih0 = oh * a.SH - a.PT; iw0 = ow * a.SW - a.PL;
+            in_img = a.in + img * ((int64_t)a.H * a.W * a.C);
+        }
+        const uint32_t lane_addr = ((uint32_t)(warp * 32)) << 16;
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t use = kb / STAGES;
+            mbar_wait(&empty[s], (use & 1) ^ 1);             // fresh barrier: passes immediately
+            if (A_TMEM) tc_fence_after();
+            unsigned char *st = smem + s * Cfg::STAGE;
+            // ---- A: 32 contiguous channels of one filter tap ----
+            uint32_t v[32];
+            {
+                const int k0 = kb * TBK;
+                const int tap = k0 / a.C, c0 = k0 - tap * a.C;
+                const int rr = tap / a.KW, ss = tap - rr * a.KW;
+                const int ih = ih0 + rr, iw = iw0 + ss;
+                const bool ok = m_ok && k0 < a.K && ih >= 0 && ih < a.H && iw >= 0 && iw < a.W;
+                const float4 *p = reinterpret_cast<const float4 *>(in_img + ((int64_t)ih * a.W + iw) * a.C + c0);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ok) x = __ldg(p + j);
+                    v[4 * j] = __float_as_uint(x.x); v[4 * j + 1] = __float_as_uint(x.y);
+                    v[4 * j + 2] = __float_as_uint(x.z); v[4 * j + 3] = __float_as_uint(x.w);
+                }
+            }
+            if (A_TMEM) {
+                uint32_t hi[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) hi[j] = v[j] & 0xFFFFE000u;
+                const uint32_t ta = tmem_base + lane_addr + BN + s * 2 * TBK;
+                tmem_st32(ta, hi);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) hi[j] = __float_as_uint(__uint_as_float(v[j]) - __uint_as_float(hi[j]));
+                tmem_st32(ta + TBK, hi);
+            } else {
+                unsigned char *ah = st, *al = st + Cfg::A_TILE;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    uint4 h, l;
+                    h.x = v[4 * j] & 0xFFFFE000u; h.y = v[4 * j + 1] & 0xFFFFE000u;
+                    h.z = v[4 * j + 2] & 0xFFFFE000u; h.w = v[4 * j + 3] & 0xFFFFE000u;
+                    l.x = __float_as_uint(__uint_as_float(v[4 * j]) - __uint_as_float(h.x));
+                    l.y = __float_as_uint(__uint_as_float(v[4 * j + 1]) - __uint_as_float(h.y));
+                    l.z = __float_as_uint(__uint_as_float(v[4 * j + 2]) - __uint_as_float(h.z));
+                    l.w = __float_as_uint(__uint_as_float(v[4 * j + 3]) - __uint_as_float(h.w));
+                    const int off = r * 128 + ((j ^ (r & 7)) << 4);
+                    *reinterpret_cast<uint4 *>(ah + off) = h;
+                    *reinterpret_cast<uint4 *>(al + off) = l;
+                }
+            }
+            // ---- B: pre-split transposed weights [N][Kp] -> [BN][32] swizzled tiles ----
+            {
+                unsigned char *bh = st + 2 * Cfg::A_TILE, *bl = bh + Cfg::B_TILE;
+                const int k0 = kb * TBK;
+#pragma unroll
+                for (int i = 0; i < (BN * 8) / 128; ++i) {
+                    const int idx = tid + i * 128;
+                    const int n = idx >> 3, j = idx & 7;
+                    const int64_t g = (int64_t)(n0 + n) * a.Kp + k0 + 4 * j;
+                    const uint4 h = __ldg(reinterpret_cast<const uint4 *>(a.wt_hi + g));
+                    const uint4 l = __ldg(reinterpret_cast<const uint4 *>(a.wt_lo + g));
+                    const int off = n * 128 + ((j ^ (n & 7)) << 4);
+                    *reinterpret_cast<uint4 *>(bh + off) = h;
+                    *reinterpret_cast<uint4 *>(bl + off) = l;
+                }
+            }
+            fence_proxy_async();                              // generic-proxy smem writes -> async proxy (UMMA)
+            if (A_TMEM) { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); tc_fence_before(); }
+            mbar_arrive(&full[s]);
+        }
+
+        // ============================ epilogue ============================
+        mbar_wait(accum, 0);
+        tc_fence_after();
+        const bool has_bias = a.flags & ISS_F_BIAS, pre = a.flags & ISS_F_AFFINE_PRE, post = a.flags & ISS_F_AFFINE_POST;
+        const bool relu = a.flags & ISS_F_RELU, resid = a.flags & ISS_F_RESIDUAL;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            uint32_t acc[32];
+            tmem_ld32(tmem_base + lane_addr + c, acc);
+            if (m_ok) {
+                float *o = a.out + m * a.N + n0 + c;
+                const float *res = resid ? a.residual + m * a.N + n0 + c : nullptr;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float x[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int n = n0 + c + j + q;
+                        float y = __uint_as_float(acc[j + q]);
+                        if (has_bias) y += __ldg(a.bias + n);
+                        if (pre) y = fmaf(y, __ldg(a.pre_scale + n), __ldg(a.pre_shift + n));
+                        if (resid) y += __ldg(res + j + q);
+                        if (relu) y = fmaxf(y, 0.f);
+                        if (post) y = fmaf(y, __ldg(a.post_scale + n), __ldg(a.post_shift + n));
+                        x[q] = y;
+                    }
+                    *reinterpret_cast<float4 *>(o + j) = make_float4(x[0], x[1], x[2], x[3]);
+                }
+            }
+        }
+        tc_fence_before();
+    } else {
+        // ============================ MMA issuer ============================
+        // instruction descriptor: D = f32, A = B = tf32, K-major both, N = BN, M = 128
+        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t use = kb / STAGES;
+            mbar_wait(&full[s], use & 1);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t st = smem_u32(smem + s * Cfg::STAGE);
+                const uint64_t dbh = make_sw128_desc(st + 2 * Cfg::A_TILE);
+                const uint64_t dbl = make_sw128_desc(st + 2 * Cfg::A_TILE + Cfg::B_TILE);
+#pragma unroll
+                for (int kk = 0; kk < TBK / 8; ++kk) {
+                    const uint32_t first = (kb > 0 || kk > 0) ? 1u : 0u;
+                    if (A_TMEM) {
+                        const uint32_t ta = tmem_base + BN + s * 2 * TBK + kk * 8;
+                        umma_tf32_ts(tmem_base, ta, dbh + 2 * kk, idesc, first);              // Ah.Bh
+                        umma_tf32_ts(tmem_base, ta, dbl + 2 * kk, idesc, 1u);                 // Ah.Bl
+                        umma_tf32_ts(tmem_base, ta + TBK, dbh + 2 * kk, idesc, 1u);           // Al.Bh
+                    } else {
+                        const uint64_t dah = make_sw128_desc(st), dal = make_sw128_desc(st + Cfg::A_TILE);
+                        umma_tf32_ss(tmem_base, dah + 2 * kk, dbh + 2 * kk, idesc, first);
+                        umma_tf32_ss(tmem_base, dah + 2 * kk, dbl + 2 * kk, idesc, 1u);
+                        umma_tf32_ss(tmem_base, dal + 2 * kk, dbh + 2 * kk, idesc, 1u);
+                    }
+                }
+                umma_commit(&empty[s]);                        // stage reusable once these MMAs have read it
+                if (kb == nkb - 1) umma_commit(accum);         // accumulator complete
+            }
+            __syncwarp();
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
+    }
+}
+
+template <int BN, int STAGES, bool A_TMEM>
+int launch_tc(const ConvArgs &a, cudaStream_t st)
+{
+    using Cfg = TcCfg<BN, STAGES, A_TMEM>;
+    auto kern = conv_gemm_tc_kernel<BN, STAGES, A_TMEM>;
+    static bool configured = false;
+    if (!configured) {
+        ISS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+        configured = true;
+    }
+    const int64_t gm = (a.M + TBM - 1) / TBM;
+    ISS_REQUIRE(gm < (1ll << 31), ISS_ERR_INVALID, "conv_tc: M too large");
+    dim3 grid((unsigned)gm, (unsigned)(a.N / BN));
+    kern<<<grid, 160, Cfg::SMEM, st>>>(a);
+    ISS_CUDA_OK(cudaGetLastError());
+    iss_count_launch();
+    return ISS_OK;
+}
+
+int g_gemm_mode = -1;      // -1 = read ISS_B200_GEMM on first use
+
+}  // namespace
+
+extern "C" int iss_set_gemm_mode(int mode)
+{
+    ISS_REQUIRE(mode >= 0 && mode <= 2, ISS_ERR_INVALID, "iss_set_gemm_mode: %d", mode);
+    g_gemm_mode = mode;
+    return ISS_OK;
+}
+
+extern "C" int iss_get_gemm_mode(void)
+{
+    if (g_gemm_mode < 0) {
+        const char *e = getenv("ISS_B200_GEMM");
+        g_gemm_mode = ISS_GEMM_DEFAULT;
+        if (e && !strcmp(e, "fp32")) g_gemm_mode = ISS_GEMM_FP32;
+        else if (e && !strcmp(e, "tc_ss")) g_gemm_mode = ISS_GEMM_TC_SS;
+        else if (e && !strcmp(e, "tc_ts")) g_gemm_mode = ISS_GEMM_TC_TS;
+    }
+    return g_gemm_mode;
+}
+
+bool iss_conv_tc_eligible(const ConvArgs &a)
+{
+    return a.wt_hi && a.wt_lo && a.Kp > 0 && a.C % 32 == 0 && a.K % 32 == 0 && a.N % 32 == 0 && a.N >= 32;
+}
+
+int iss_launch_conv_tc(const ConvArgs &a, int mode, cudaStream_t st)
+{
+    const bool ts = (mode == ISS_GEMM_TC_TS);
+    // BN: the widest of {256,128,64,32} dividing N
+    if (a.N % 256 == 0) return ts ? launch_tc<256, 2, true>(a, st) : launch_tc<256, 2, false>(a, st);
+    if (a.N % 128 == 0) return ts ? launch_tc<128, 2, true>(a, st) : launch_tc<128, 2, false>(a, st);
+    if (a.N % 64 == 0) return ts ? launch_tc<64, 3, true>(a, st) : launch_tc<64, 2, false>(a, st);
+    return ts ? launch_tc<32, 3, true>(a, st) : launch_tc<32, 3, false>(a, st);
+}
+
+// Host-side preparation of a layer's weights for the tensor-core path:
+// W[K][N] (Keras / our blob layout) -> transposed, zero-padded, split [2][N][Kp].
+int iss_prepare_tc_weights(const float *h_w, int K, int N, float **d_out, int *Kp_out)
+{
+    const int Kp = (K + TBK - 1) / TBK * TBK;
+    std::vector<float> buf((size_t)2 * N * Kp, 0.f);
+    float *hi = buf.data(), *lo = buf.data() + (size_t)N * Kp;
+    for (int k = 0; k < K; ++k)
+        for (int n = 0; n < N; ++n) {
+            const float w = h_w[(size_t)k * N + n];
+            uint32_t u;
+            memcpy(&u, &w, 4);
+            u &= 0xFFFFE000u;
+            float h;
+            memcpy(&h, &u, 4);
+            hi[(size_t)n * Kp + k] = h;
+            lo[(size_t)n * Kp + k] = w - h;
+        }
+    float *d = nullptr;
+    cudaError_t e = cudaMalloc(&d, buf.size() * sizeof(float));
+    if (e != cudaSuccess) { iss_set_error("cudaMalloc tc weights: %s", cudaGetErrorString(e)); return ISS_ERR_NOMEM; }
+    e = cudaMemcpy(d, buf.data(), buf.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(d); iss_set_error("cudaMemcpy tc weights: %s", cudaGetErrorString(e)); return ISS_ERR_CUDA; }
+    *d_out = d;
+    *Kp_out = Kp;
+    return ISS_OK;
+}

@@ -24,6 +24,8 @@ namespace {
 struct RConv {
     int kh, kw, stride, pad, cin, cout;
     int64_t w_off, scale_off, shift_off;
+    float *d_wt = nullptr;      // tensor-core weights [2][N][Kp]
+    int Kp = 0;
 };
 
 struct RBlock {
@@ -74,6 +76,8 @@ struct iss_resnet {
     std::vector<RBlock> blocks;
     int64_t emb_w_off, emb_b_off;
     int c_final, h_final;
+    float *d_emb_wt = nullptr;
+    int emb_Kp = 0;
 };
 
 namespace {
@@ -85,7 +89,8 @@ int64_t build_plan(int m, int feat_dim, int embed_dim, const int *nb, iss_resnet
 {
     int64_t off = 0;
     auto mk = [&](int k, int stride, int pad, int cin, int cout) {
-        RConv c{k, k, stride, pad, cin, cout, 0, 0, 0};
+        RConv c;
+        c.kh = k; c.kw = k; c.stride = stride; c.pad = pad; c.cin = cin; c.cout = cout;
         c.w_off = off; off += (int64_t)k * k * cin * cout;
         c.scale_off = off; off += cout;
         c.shift_off = off; off += cout;
@@ -151,6 +156,8 @@ extern "C" int64_t iss_resnet_blob_len(int m_channels, int feat_dim, int embed_d
     return build_plan(m_channels, feat_dim, embed_dim, num_blocks, nullptr);
 }
 
+extern "C" int iss_resnet_destroy(iss_resnet *net);
+
 extern "C" int iss_resnet_create(iss_ctx *ctx, const float *h_blob, int64_t blob_len, int m_channels, int feat_dim,
                                  int embed_dim, const int *num_blocks, iss_resnet **out)
 {
@@ -170,6 +177,23 @@ extern "C" int iss_resnet_create(iss_ctx *ctx, const float *h_blob, int64_t blob
     if (e != cudaSuccess) { delete net; iss_set_error("cudaMalloc resnet blob: %s", cudaGetErrorString(e)); return ISS_ERR_NOMEM; }
     e = cudaMemcpy(net->d_blob, h_blob, (size_t)blob_len * sizeof(float), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaFree(net->d_blob); delete net; iss_set_error("cudaMemcpy resnet blob: %s", cudaGetErrorString(e)); return ISS_ERR_CUDA; }
+    auto prep = [&](RConv &c) -> int {
+        const int K = c.kh * c.kw * c.cin;
+        if (c.cin % 32 != 0 || K % 32 != 0 || c.cout % 32 != 0) return ISS_OK;
+        return iss_prepare_tc_weights(h_blob + c.w_off, K, c.cout, &c.d_wt, &c.Kp);
+    };
+    int prc = ISS_OK;
+    for (RBlock &b : net->blocks) {
+        if (prc == ISS_OK) prc = prep(b.c1);
+        if (prc == ISS_OK) prc = prep(b.c2);
+        if (prc == ISS_OK) prc = prep(b.c3);
+        if (prc == ISS_OK && b.has_sc) prc = prep(b.sc);
+    }
+    if (prc == ISS_OK) {
+        const int K = 2 * net->c_final * net->h_final;
+        prc = iss_prepare_tc_weights(h_blob + net->emb_w_off, K, net->embed_dim, &net->d_emb_wt, &net->emb_Kp);
+    }
+    if (prc != ISS_OK) { iss_resnet_destroy(net); return prc; }
     *out = net;
     return ISS_OK;
 }
@@ -179,6 +203,13 @@ extern "C" int iss_resnet_destroy(iss_resnet *net)
     if (!net) return ISS_OK;
     cudaSetDevice(net->ctx->device);
     if (net->d_blob) cudaFree(net->d_blob);
+    if (net->d_emb_wt) cudaFree(net->d_emb_wt);
+    for (RBlock &b : net->blocks) {
+        if (b.c1.d_wt) cudaFree(b.c1.d_wt);
+        if (b.c2.d_wt) cudaFree(b.c2.d_wt);
+        if (b.c3.d_wt) cudaFree(b.c3.d_wt);
+        if (b.has_sc && b.sc.d_wt) cudaFree(b.sc.d_wt);
+    }
     delete net;
     return ISS_OK;
 }
@@ -238,6 +269,7 @@ extern "C" int iss_resnet_embed(iss_ctx *ctx, iss_resnet *net, const float *d_fe
         ConvArgs a = {};
         a.in = in; a.w = blob + c.w_off; a.pre_scale = blob + c.scale_off; a.pre_shift = blob + c.shift_off;
         a.residual = residual; a.out = out;
+        if (c.d_wt) { a.wt_hi = c.d_wt; a.wt_lo = c.d_wt + (size_t)c.cout * c.Kp; a.Kp = c.Kp; }
         a.M = (int64_t)nb * oh * ow; a.N = c.cout; a.K = c.kh * c.kw * c.cin;
         a.H = h; a.W = w; a.C = c.cin; a.OH = oh; a.OW = ow;
         a.KH = c.kh; a.KW = c.kw; a.SH = c.stride; a.SW = c.stride; a.PT = c.pad; a.PL = c.pad;
@@ -275,6 +307,7 @@ extern "C" int iss_resnet_embed(iss_ctx *ctx, iss_resnet *net, const float *d_fe
         a.M = nb; a.N = net->embed_dim; a.K = 2 * net->c_final * h;
         a.H = 1; a.W = 1; a.C = a.K; a.OH = 1; a.OW = 1; a.KH = 1; a.KW = 1; a.SH = 1; a.SW = 1;
         a.flags = ISS_F_BIAS;
+        if (net->d_emb_wt) { a.wt_hi = net->d_emb_wt; a.wt_lo = net->d_emb_wt + (size_t)net->embed_dim * net->emb_Kp; a.Kp = net->emb_Kp; }
         rc = iss_launch_conv(a, false, st);
         if (rc != ISS_OK) return rc;
     }

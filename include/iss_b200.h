@@ -48,6 +48,13 @@ int iss_ctx_destroy(iss_ctx *ctx);
 /* Number of kernels this library has launched in this process so far (all
  * contexts); bench.py reports the delta over its timed region. */
 int64_t iss_launch_count(void);
+/* GEMM engine used by the conv / dense layers of K2 and K5 (process-wide):
+ * 0 = fp32 CUDA cores, 1 = tcgen05 3xTF32 with both operands in shared memory,
+ * 2 = tcgen05 3xTF32 with the activation operand in tensor memory.  All three
+ * are sm_100a code paths of this library with fp32-class accuracy; the default
+ * can be overridden with the environment variable ISS_B200_GEMM=fp32|tc_ss|tc_ts. */
+int iss_set_gemm_mode(int mode);
+int iss_get_gemm_mode(void);
 
 /* ---- K1: SIDEKIT log-mel + log-energy front-end -------------------------
  * Replaces mfcc(sig, get_mspec=True) as used by _media2feats
