@@ -131,13 +131,13 @@ struct TcCfg {
     static constexpr int A_TILE = A_TMEM ? 0 : TBM * TBK * 4;           // bytes per hi (or lo) A tile in smem
     static constexpr int B_TILE = BN * TBK * 4;
     static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
-    static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/ + 4 * 4096 /*per-warp transpose*/;
     static constexpr uint32_t TMEM_USED = BN + (A_TMEM ? STAGES * 2 * TBK : 0);
     static constexpr uint32_t TMEM_COLS = tmem_cols_pow2(TMEM_USED);
 };
 
 template <int BN, int STAGES, bool A_TMEM>
-__global__ void __launch_bounds__(160)
+__global__ void __launch_bounds__(160, (BN <= 128 ? 2 : 1))
 conv_gemm_tc_kernel(const ConvArgs a)
 {
     using Cfg = TcCfg<BN, STAGES, A_TMEM>;
@@ -168,46 +168,61 @@ conv_gemm_tc_kernel(const ConvArgs a)
 
     if (warp < 4) {
         // ============================ producers ============================
-        const int r = tid;                                   // A row in the tile == TMEM lane
-        const int64_t m = m0 + r;
-        const bool m_ok = m < a.M;
-        int ih0 = 0, iw0 = 0;
-        const float *in_img = a.in;
-        {
-            const int64_t mm = m_ok ? m : 0;
+        // Coalesced gather: for load i (0..7) lane l fetches 16-byte chunk (l & 7) of tile row
+        // 32*warp + 4*i + (l >> 3), so one warp instruction reads 4 full 128-byte segments
+        // (4 L1 wavefronts instead of 32).  Rows are then regrouped per lane through a
+        // warp-private swizzled 4 KB staging buffer (TS mode) or written straight to the
+        // swizzled operand tile (SS mode).
+        const int sub = lane >> 3, chunk = lane & 7;
+        int64_t row_off[8];                                  // element offset of the (img, ih0, iw0) origin
+        int row_ih0[8], row_iw0[8];
+        bool row_ok[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int64_t m = m0 + warp * 32 + 4 * i + sub;
+            row_ok[i] = m < a.M;
+            const int64_t mm = row_ok[i] ? m : 0;
             const int ohw = a.OH * a.OW;
             const int64_t img = mm / ohw;
             const int rem = (int)(mm - img * ohw);
             const int oh = rem / a.OW, ow = rem - oh * a.OW;
-            ih0 = oh * a.SH - a.PT; iw0 = ow * a.SW - a.PL;
-            in_img = a.in + img * ((int64_t)a.H * a.W * a.C);
+            row_ih0[i] = oh * a.SH - a.PT; row_iw0[i] = ow * a.SW - a.PL;
+            row_off[i] = img * ((int64_t)a.H * a.W * a.C) + ((int64_t)row_ih0[i] * a.W + row_iw0[i]) * a.C;
         }
+        unsigned char *stage_buf = smem + STAGES * Cfg::STAGE + 256 + warp * 4096;   // warp-private transpose buffer
         const uint32_t lane_addr = ((uint32_t)(warp * 32)) << 16;
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % STAGES;
             const uint32_t use = kb / STAGES;
+            const int k0 = kb * TBK;
+            const int tap = k0 / a.C, c0 = k0 - tap * a.C;
+            const int rr = tap / a.KW, ss = tap - rr * a.KW;
+            const int64_t tap_off = ((int64_t)rr * a.W + ss) * a.C + c0 + chunk * 4;
+            uint4 x[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int ih = row_ih0[i] + rr, iw = row_iw0[i] + ss;
+                const bool ok = row_ok[i] && ih >= 0 && ih < a.H && iw >= 0 && iw < a.W;
+                x[i] = make_uint4(0u, 0u, 0u, 0u);
+                if (ok) x[i] = __ldg(reinterpret_cast<const uint4 *>(a.in + row_off[i] + tap_off));
+            }
             mbar_wait(&empty[s], (use & 1) ^ 1);             // fresh barrier: passes immediately
-            if (A_TMEM) tc_fence_after();
             unsigned char *st = smem + s * Cfg::STAGE;
-            // ---- A: 32 contiguous channels of one filter tap ----
-            uint32_t v[32];
-            {
-                const int k0 = kb * TBK;
-                const int tap = k0 / a.C, c0 = k0 - tap * a.C;
-                const int rr = tap / a.KW, ss = tap - rr * a.KW;
-                const int ih = ih0 + rr, iw = iw0 + ss;
-                const bool ok = m_ok && k0 < a.K && ih >= 0 && ih < a.H && iw >= 0 && iw < a.W;
-                const float4 *p = reinterpret_cast<const float4 *>(in_img + ((int64_t)ih * a.W + iw) * a.C + c0);
+            if (A_TMEM) {
+                tc_fence_after();
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int rl = 4 * i + sub;
+                    *reinterpret_cast<uint4 *>(stage_buf + rl * 128 + ((chunk ^ (rl & 7)) << 4)) = x[i];
+                }
+                __syncwarp();
+                uint32_t v[32], hi[32];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (ok) x = __ldg(p + j);
-                    v[4 * j] = __float_as_uint(x.x); v[4 * j + 1] = __float_as_uint(x.y);
-                    v[4 * j + 2] = __float_as_uint(x.z); v[4 * j + 3] = __float_as_uint(x.w);
+                    const uint4 q = *reinterpret_cast<const uint4 *>(stage_buf + lane * 128 + ((j ^ (lane & 7)) << 4));
+                    v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
                 }
-            }
-            if (A_TMEM) {
-                uint32_t hi[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) hi[j] = v[j] & 0xFFFFE000u;
                 const uint32_t ta = tmem_base + lane_addr + BN + s * 2 * TBK;
@@ -218,15 +233,15 @@ conv_gemm_tc_kernel(const ConvArgs a)
             } else {
                 unsigned char *ah = st, *al = st + Cfg::A_TILE;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int i = 0; i < 8; ++i) {
+                    const int r = warp * 32 + 4 * i + sub;
                     uint4 h, l;
-                    h.x = v[4 * j] & 0xFFFFE000u; h.y = v[4 * j + 1] & 0xFFFFE000u;
-                    h.z = v[4 * j + 2] & 0xFFFFE000u; h.w = v[4 * j + 3] & 0xFFFFE000u;
-                    l.x = __float_as_uint(__uint_as_float(v[4 * j]) - __uint_as_float(h.x));
-                    l.y = __float_as_uint(__uint_as_float(v[4 * j + 1]) - __uint_as_float(h.y));
-                    l.z = __float_as_uint(__uint_as_float(v[4 * j + 2]) - __uint_as_float(h.z));
-                    l.w = __float_as_uint(__uint_as_float(v[4 * j + 3]) - __uint_as_float(h.w));
-                    const int off = r * 128 + ((j ^ (r & 7)) << 4);
+                    h.x = x[i].x & 0xFFFFE000u; h.y = x[i].y & 0xFFFFE000u; h.z = x[i].z & 0xFFFFE000u; h.w = x[i].w & 0xFFFFE000u;
+                    l.x = __float_as_uint(__uint_as_float(x[i].x) - __uint_as_float(h.x));
+                    l.y = __float_as_uint(__uint_as_float(x[i].y) - __uint_as_float(h.y));
+                    l.z = __float_as_uint(__uint_as_float(x[i].z) - __uint_as_float(h.z));
+                    l.w = __float_as_uint(__uint_as_float(x[i].w) - __uint_as_float(h.w));
+                    const int off = r * 128 + ((chunk ^ (r & 7)) << 4);
                     *reinterpret_cast<uint4 *>(ah + off) = h;
                     *reinterpret_cast<uint4 *>(al + off) = l;
                 }
@@ -234,7 +249,6 @@ conv_gemm_tc_kernel(const ConvArgs a)
             // ---- B: pre-split transposed weights [N][Kp] -> [BN][32] swizzled tiles ----
             {
                 unsigned char *bh = st + 2 * Cfg::A_TILE, *bl = bh + Cfg::B_TILE;
-                const int k0 = kb * TBK;
 #pragma unroll
                 for (int i = 0; i < (BN * 8) / 128; ++i) {
                     const int idx = tid + i * 128;
@@ -253,6 +267,9 @@ conv_gemm_tc_kernel(const ConvArgs a)
         }
 
         // ============================ epilogue ============================
+        // TMEM quadrant -> registers (lane = row) -> swizzled staging -> coalesced rows:
+        // lane l then owns columns 4*(l&7)..+3 of rows 4*i + (l>>3), so bias / BN vectors are
+        // per-lane constants and every store instruction writes four full 128-byte segments.
         mbar_wait(accum, 0);
         tc_fence_after();
         const bool has_bias = a.flags & ISS_F_BIAS, pre = a.flags & ISS_F_AFFINE_PRE, post = a.flags & ISS_F_AFFINE_POST;
@@ -261,24 +278,40 @@ conv_gemm_tc_kernel(const ConvArgs a)
         for (int c = 0; c < BN; c += 32) {
             uint32_t acc[32];
             tmem_ld32(tmem_base + lane_addr + c, acc);
-            if (m_ok) {
-                float *o = a.out + m * a.N + n0 + c;
-                const float *res = resid ? a.residual + m * a.N + n0 + c : nullptr;
+            __syncwarp();
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float x[4];
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<uint4 *>(stage_buf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                    make_uint4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+            __syncwarp();
+            const int nb = n0 + c + chunk * 4;
+            float eb[4], es1[4], et1[4], es2[4], et2[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                eb[q] = has_bias ? __ldg(a.bias + nb + q) : 0.f;
+                es1[q] = pre ? __ldg(a.pre_scale + nb + q) : 1.f;  et1[q] = pre ? __ldg(a.pre_shift + nb + q) : 0.f;
+                es2[q] = post ? __ldg(a.post_scale + nb + q) : 1.f; et2[q] = post ? __ldg(a.post_shift + nb + q) : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int rl = 4 * i + sub;
+                const int64_t m = m0 + warp * 32 + rl;
+                const uint4 q4 = *reinterpret_cast<const uint4 *>(stage_buf + rl * 128 + ((chunk ^ (rl & 7)) << 4));
+                if (m < a.M) {
+                    float y[4] = {__uint_as_float(q4.x), __uint_as_float(q4.y), __uint_as_float(q4.z), __uint_as_float(q4.w)};
+                    float4 rs = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (resid) rs = __ldg(reinterpret_cast<const float4 *>(a.residual + m * a.N + nb));
+                    const float rv[4] = {rs.x, rs.y, rs.z, rs.w};
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const int n = n0 + c + j + q;
-                        float y = __uint_as_float(acc[j + q]);
-                        if (has_bias) y += __ldg(a.bias + n);
-                        if (pre) y = fmaf(y, __ldg(a.pre_scale + n), __ldg(a.pre_shift + n));
-                        if (resid) y += __ldg(res + j + q);
-                        if (relu) y = fmaxf(y, 0.f);
-                        if (post) y = fmaf(y, __ldg(a.post_scale + n), __ldg(a.post_shift + n));
-                        x[q] = y;
+                        float t = y[q] + eb[q];
+                        if (pre) t = fmaf(t, es1[q], et1[q]);
+                        if (resid) t += rv[q];
+                        if (relu) t = fmaxf(t, 0.f);
+                        if (post) t = fmaf(t, es2[q], et2[q]);
+                        y[q] = t;
                     }
-                    *reinterpret_cast<float4 *>(o + j) = make_float4(x[0], x[1], x[2], x[3]);
+                    *reinterpret_cast<float4 *>(a.out + m * a.N + nb) = make_float4(y[0], y[1], y[2], y[3]);
                 }
             }
         }
