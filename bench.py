@@ -294,7 +294,8 @@ def run_b200(args):
     peak_tf = peaks.get('bf16_tflops_sustained') or 1400.0
     peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)' if 'bf16_tflops_sustained' in peaks else 'fallback 1.4 PFLOP/s sustained (of fallback)'
     ach = (fl.value / max(nlaunch.value, 1)) / (tms.value / max(nlaunch.value, 1) * 1e-3) / 1e12 if tms.value > 0 else 0.0
-    roof = {'bound': 'tensor', 'kernel': 'conv_gemm (VAD layer %d: %s)' % (dom, layer_name(seg.vad.nn.lowered.descs[dom])),
+    gemm = {0: 'fp32 CUDA cores', 1: 'tcgen05 3xTF32 (A,B from smem)', 2: 'tcgen05 3xTF32 (A from TMEM)'}[lib.iss_get_gemm_mode()]
+    roof = {'bound': 'tensor', 'kernel': 'conv_gemm %s (VAD layer %d: %s)' % (gemm, dom, layer_name(seg.vad.nn.lowered.descs[dom])),
             'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf, 'traffic': None,
             'peak_source': peak_src, 'launches': int(nlaunch.value), 'avg_launch_ms': tms.value / max(nlaunch.value, 1),
             'flops_per_launch': fl.value / max(nlaunch.value, 1), 'share_of_step': tms.value / ms}
@@ -302,7 +303,7 @@ def run_b200(args):
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f32', 'data': 'synthetic',
+        'dtype': 'f32' if lib.iss_get_gemm_mode() == 0 else 'f32 (3xTF32 split on tcgen05, fp32 accumulate)', 'data': 'synthetic',
         'config': {'workload': 'smn+gender on %g h synthetic 16 kHz mono int16 per GPU (BASELINE configs[1])' % args.hours,
                    'networks': 'synthetic-weight stand-ins of the ~1.4M-parameter CNN family (release .hdf5 absent)',
                    'fft': args.fft, 'l2': 'inputs larger than L2 (%.2f GB PCM per step)' % (pcm.numel() * 2 / 1e9),

@@ -28,7 +28,7 @@ struct ConvArgs {
 #define ISS_GEMM_TC_SS 1      /* tcgen05 3xTF32, A and B from shared memory */
 #define ISS_GEMM_TC_TS 2      /* tcgen05 3xTF32, A from tensor memory, B from shared memory */
 #ifndef ISS_GEMM_DEFAULT
-#define ISS_GEMM_DEFAULT ISS_GEMM_FP32
+#define ISS_GEMM_DEFAULT ISS_GEMM_TC_TS
 #endif
 
 extern "C" int iss_get_gemm_mode(void);

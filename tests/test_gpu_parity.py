@@ -194,6 +194,29 @@ def test_k2_cnn_softmax_vs_oracle(rt, synth_models, which, nmel):
     assert err <= 1e-4, err
 
 
+@pytest.mark.parametrize('mode', [0, 1, 2])
+def test_k2_all_gemm_engines_vs_oracle(rt, synth_models, mode):
+    """fp32 CUDA-core kernel and both tcgen05 3xTF32 variants against the fp32 oracle (1e-4)."""
+    from oracle import sidekit_oracle as sk
+    lib = rt['lib'].load()
+    prev = lib.iss_get_gemm_mode()
+    try:
+        rt['lib'].check(lib.iss_set_gemm_mode(mode), 'set mode')
+        cfg, w = synth_models['gender']
+        sig = synth_audio(30, seed=17).astype(np.float32) / np.float32(32768)
+        mspec, loge = sk.logmel_loge(sig)
+        P = (len(loge) + 1) // 2
+        ranges = [(0, 300), (P - 257, P)]
+        ref = _oracle_probs(cfg, w, mspec, 24, ranges)
+        net = rt['engine'].CnnModel.from_keras(rt['ctx'], cfg, w, 24)
+        got = net.forward(torch.from_numpy(mspec).cuda(), ranges).cpu().numpy()
+        err = np.abs(got - ref).max()
+        REPORT['k2_gender_gemm_mode%d' % mode] = dict(softmax_max_abs=float(err))
+        assert err <= 1e-4, err
+    finally:
+        lib.iss_set_gemm_mode(prev)
+
+
 @pytest.mark.parametrize('L', [68, 69, 70, 101, 135, 136])
 def test_k2_edge_replication(rt, synth_models, L):
     cfg, w = synth_models['sm']
