@@ -132,12 +132,13 @@ struct TcCfg {
     static constexpr int B_TILE = BN * TBK * 4;
     static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
     static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/ + 4 * 4096 /*per-warp transpose*/;
-    static constexpr uint32_t TMEM_USED = BN + (A_TMEM ? STAGES * 2 * TBK : 0);
+    static constexpr uint32_t ACC_COLS = 2 * BN;                        // D_main | D_lo (correction terms)
+    static constexpr uint32_t TMEM_USED = ACC_COLS + (A_TMEM ? STAGES * 2 * TBK : 0);
     static constexpr uint32_t TMEM_COLS = tmem_cols_pow2(TMEM_USED);
 };
 
 template <int BN, int STAGES, bool A_TMEM>
-__global__ void __launch_bounds__(160, (BN <= 128 ? 2 : 1))
+__global__ void __launch_bounds__(160, (BN <= 64 ? 2 : 1))
 conv_gemm_tc_kernel(const ConvArgs a)
 {
     using Cfg = TcCfg<BN, STAGES, A_TMEM>;
@@ -225,7 +226,7 @@ conv_gemm_tc_kernel(const ConvArgs a)
                 }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) hi[j] = v[j] & 0xFFFFE000u;
-                const uint32_t ta = tmem_base + lane_addr + BN + s * 2 * TBK;
+                const uint32_t ta = tmem_base + lane_addr + Cfg::ACC_COLS + s * 2 * TBK;
                 tmem_st32(ta, hi);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) hi[j] = __float_as_uint(__uint_as_float(v[j]) - __uint_as_float(hi[j]));
@@ -277,7 +278,13 @@ conv_gemm_tc_kernel(const ConvArgs a)
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
             uint32_t acc[32];
-            tmem_ld32(tmem_base + lane_addr + c, acc);
+            {
+                uint32_t corr[32];
+                tmem_ld32(tmem_base + lane_addr + c, acc);
+                tmem_ld32(tmem_base + lane_addr + BN + c, corr);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(corr[j]));
+            }
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < 8; ++j)
@@ -332,16 +339,21 @@ conv_gemm_tc_kernel(const ConvArgs a)
 #pragma unroll
                 for (int kk = 0; kk < TBK / 8; ++kk) {
                     const uint32_t first = (kb > 0 || kk > 0) ? 1u : 0u;
+                    // The tensor core's accumulate-add truncates, so every MMA into an accumulator
+                    // costs ~half an ulp of bias relative to that accumulator's magnitude: the two
+                    // small correction products go to their own accumulator (D_lo) and are added
+                    // to D_main with a correctly rounded fp32 add in the epilogue.
+                    const uint32_t d_main = tmem_base, d_lo = tmem_base + BN;
                     if (A_TMEM) {
-                        const uint32_t ta = tmem_base + BN + s * 2 * TBK + kk * 8;
-                        umma_tf32_ts(tmem_base, ta, dbh + 2 * kk, idesc, first);              // Ah.Bh
-                        umma_tf32_ts(tmem_base, ta, dbl + 2 * kk, idesc, 1u);                 // Ah.Bl
-                        umma_tf32_ts(tmem_base, ta + TBK, dbh + 2 * kk, idesc, 1u);           // Al.Bh
+                        const uint32_t ta = tmem_base + Cfg::ACC_COLS + s * 2 * TBK + kk * 8;
+                        umma_tf32_ts(d_main, ta, dbh + 2 * kk, idesc, first);                 // Ah.Bh
+                        umma_tf32_ts(d_lo, ta, dbl + 2 * kk, idesc, first);                   // Ah.Bl
+                        umma_tf32_ts(d_lo, ta + TBK, dbh + 2 * kk, idesc, 1u);                // Al.Bh
                     } else {
                         const uint64_t dah = make_sw128_desc(st), dal = make_sw128_desc(st + Cfg::A_TILE);
-                        umma_tf32_ss(tmem_base, dah + 2 * kk, dbh + 2 * kk, idesc, first);
-                        umma_tf32_ss(tmem_base, dah + 2 * kk, dbl + 2 * kk, idesc, 1u);
-                        umma_tf32_ss(tmem_base, dal + 2 * kk, dbh + 2 * kk, idesc, 1u);
+                        umma_tf32_ss(d_main, dah + 2 * kk, dbh + 2 * kk, idesc, first);
+                        umma_tf32_ss(d_lo, dah + 2 * kk, dbl + 2 * kk, idesc, first);
+                        umma_tf32_ss(d_lo, dal + 2 * kk, dbh + 2 * kk, idesc, 1u);
                     }
                 }
                 umma_commit(&empty[s]);                        // stage reusable once these MMAs have read it
@@ -409,9 +421,9 @@ int iss_launch_conv_tc(const ConvArgs &a, int mode, cudaStream_t st)
 {
     const bool ts = (mode == ISS_GEMM_TC_TS);
     // BN: the widest of {256,128,64,32} dividing N
-    if (a.N % 256 == 0) return ts ? launch_tc<256, 2, true>(a, st) : launch_tc<256, 2, false>(a, st);
-    if (a.N % 128 == 0) return ts ? launch_tc<128, 2, true>(a, st) : launch_tc<128, 2, false>(a, st);
-    if (a.N % 64 == 0) return ts ? launch_tc<64, 3, true>(a, st) : launch_tc<64, 2, false>(a, st);
+    // two accumulators per tile (main + correction) => BN <= 128 (2 x 128 + A ring <= 512 TMEM columns)
+    if (a.N % 128 == 0) return ts ? launch_tc<128, 3, true>(a, st) : launch_tc<128, 2, false>(a, st);
+    if (a.N % 64 == 0) return ts ? launch_tc<64, 2, true>(a, st) : launch_tc<64, 2, false>(a, st);
     return ts ? launch_tc<32, 3, true>(a, st) : launch_tc<32, 3, false>(a, st);
 }
 
