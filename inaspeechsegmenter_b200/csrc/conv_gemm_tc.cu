@@ -370,6 +370,269 @@ conv_gemm_tc_kernel(const ConvArgs a)
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Asynchronous TS pipeline (the production path).  Differences from the kernel above:
+//   * A rows are fetched with cp.async (16-byte, L2 -> smem, zero-fill for padding / tail rows)
+//     into a warp-private DA-deep ring, so DA k-blocks of gathers are in flight per warp with no
+//     register staging; the ring doubles as the transpose buffer (lane = row on the way out).
+//   * the weight tiles are fetched by the MMA warp itself (32 lanes of cp.async into an SB-deep
+//     ring), which removes them from the producers' critical path;
+//   * operand A goes registers -> TMEM (tcgen05.st) into an ST-deep ring next to the two
+//     accumulators, so shared memory only carries B for the MMAs.
+template <int BN, int DA, int SB, int ST>
+struct Tc2Cfg {
+    static constexpr int A_SLOT = 4096;                                  // 32 rows x 128 B per warp
+    static constexpr int A_RING = 4 * DA * A_SLOT;
+    static constexpr int B_TILE = BN * TBK * 4;
+    static constexpr int B_STAGE = 2 * B_TILE;                           // hi | lo
+    static constexpr int SMEM = A_RING + SB * B_STAGE + 1024 + 256;
+    static constexpr uint32_t ACC_COLS = 2 * BN;
+    static constexpr uint32_t TMEM_COLS = tmem_cols_pow2(ACC_COLS + ST * 2 * TBK);
+};
+
+__device__ __forceinline__ void cp_async16(void *dst, const void *src, int src_bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int BN, int DA, int SB, int ST>
+__global__ void __launch_bounds__(160, (BN <= 64 ? 2 : 1))
+conv_gemm_tc2_kernel(const ConvArgs a)
+{
+    using Cfg = Tc2Cfg<BN, DA, SB, ST>;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    unsigned char *b_ring = smem;                                        // 1024-aligned operand tiles first
+    unsigned char *a_ring = smem + SB * Cfg::B_STAGE;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(a_ring + Cfg::A_RING);
+    uint64_t *fullA = bars, *emptyA = bars + ST, *emptyB = bars + 2 * ST, *accum = bars + 2 * ST + SB;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * ST + SB + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t m0 = (int64_t)blockIdx.x * TBM;
+    const int n0 = blockIdx.y * BN;
+    const int nkb = a.Kp / TBK;
+
+    if (tid == 0) {
+        for (int s = 0; s < ST; ++s) { mbar_init(&fullA[s], 128); mbar_init(&emptyA[s], 1); }
+        for (int s = 0; s < SB; ++s) mbar_init(&emptyB[s], 1);
+        mbar_init(accum, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // ============================ A producers ============================
+        const int sub = lane >> 3, chunk = lane & 7;
+        int64_t row_off[8];
+        int row_ih0[8], row_iw0[8];
+        bool row_ok[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int64_t m = m0 + warp * 32 + 4 * i + sub;
+            row_ok[i] = m < a.M;
+            const int64_t mm = row_ok[i] ? m : 0;
+            const int ohw = a.OH * a.OW;
+            const int64_t img = mm / ohw;
+            const int rem = (int)(mm - img * ohw);
+            const int oh = rem / a.OW, ow = rem - oh * a.OW;
+            row_ih0[i] = oh * a.SH - a.PT; row_iw0[i] = ow * a.SW - a.PL;
+            row_off[i] = img * ((int64_t)a.H * a.W * a.C) + ((int64_t)row_ih0[i] * a.W + row_iw0[i]) * a.C;
+        }
+        unsigned char *my_ring = a_ring + warp * DA * Cfg::A_SLOT;
+        auto issue_a = [&](int kb) {
+            if (kb < nkb) {
+                const int k0 = kb * TBK;
+                const int tap = k0 / a.C, c0 = k0 - tap * a.C;
+                const int rr = tap / a.KW, ss = tap - rr * a.KW;
+                const int64_t tap_off = ((int64_t)rr * a.W + ss) * a.C + c0 + chunk * 4;
+                unsigned char *slot = my_ring + (kb % DA) * Cfg::A_SLOT;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int ih = row_ih0[i] + rr, iw = row_iw0[i] + ss;
+                    const bool ok = row_ok[i] && ih >= 0 && ih < a.H && iw >= 0 && iw < a.W;
+                    const int rl = 4 * i + sub;
+                    cp_async16(slot + rl * 128 + ((chunk ^ (rl & 7)) << 4), ok ? (const void *)(a.in + row_off[i] + tap_off) : (const void *)a.in,
+                               ok ? 16 : 0);
+                }
+            }
+            cp_async_commit();
+        };
+#pragma unroll
+        for (int p = 0; p < DA; ++p) issue_a(p);
+        const uint32_t lane_addr = ((uint32_t)(warp * 32)) << 16;
+        for (int kb = 0; kb < nkb; ++kb) {
+            cp_async_wait<DA - 1>();
+            __syncwarp();
+            const unsigned char *slot = my_ring + (kb % DA) * Cfg::A_SLOT;
+            uint32_t v[32], hi[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint4 q = *reinterpret_cast<const uint4 *>(slot + lane * 128 + ((j ^ (lane & 7)) << 4));
+                v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+            }
+            __syncwarp();                                    // slot fully read before it is refilled
+            issue_a(kb + DA);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) hi[j] = v[j] & 0xFFFFE000u;
+            const int st = kb % ST;
+            mbar_wait(&emptyA[st], ((kb / ST) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t ta = tmem_base + lane_addr + Cfg::ACC_COLS + st * 2 * TBK;
+            tmem_st32(ta, hi);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) hi[j] = __float_as_uint(__uint_as_float(v[j]) - __uint_as_float(hi[j]));
+            tmem_st32(ta + TBK, hi);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            mbar_arrive(&fullA[st]);
+        }
+        cp_async_wait<0>();
+
+        // ============================ epilogue ============================
+        mbar_wait(accum, 0);
+        tc_fence_after();
+        unsigned char *stage_buf = my_ring;                  // the A ring is idle now: reuse slot 0 as transpose buffer
+        const bool has_bias = a.flags & ISS_F_BIAS, pre = a.flags & ISS_F_AFFINE_PRE, post = a.flags & ISS_F_AFFINE_POST;
+        const bool relu = a.flags & ISS_F_RELU, resid = a.flags & ISS_F_RESIDUAL;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            uint32_t acc[32];
+            {
+                uint32_t corr[32];
+                tmem_ld32(tmem_base + lane_addr + c, acc);
+                tmem_ld32(tmem_base + lane_addr + BN + c, corr);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(corr[j]));
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<uint4 *>(stage_buf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                    make_uint4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+            __syncwarp();
+            const int nb = n0 + c + chunk * 4;
+            float eb[4], es1[4], et1[4], es2[4], et2[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                eb[q] = has_bias ? __ldg(a.bias + nb + q) : 0.f;
+                es1[q] = pre ? __ldg(a.pre_scale + nb + q) : 1.f;  et1[q] = pre ? __ldg(a.pre_shift + nb + q) : 0.f;
+                es2[q] = post ? __ldg(a.post_scale + nb + q) : 1.f; et2[q] = post ? __ldg(a.post_shift + nb + q) : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int rl = 4 * i + sub;
+                const int64_t m = m0 + warp * 32 + rl;
+                const uint4 q4 = *reinterpret_cast<const uint4 *>(stage_buf + rl * 128 + ((chunk ^ (rl & 7)) << 4));
+                if (m < a.M) {
+                    float y[4] = {__uint_as_float(q4.x), __uint_as_float(q4.y), __uint_as_float(q4.z), __uint_as_float(q4.w)};
+                    float4 rs = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (resid) rs = __ldg(reinterpret_cast<const float4 *>(a.residual + m * a.N + nb));
+                    const float rv[4] = {rs.x, rs.y, rs.z, rs.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float t = y[q] + eb[q];
+                        if (pre) t = fmaf(t, es1[q], et1[q]);
+                        if (resid) t += rv[q];
+                        if (relu) t = fmaxf(t, 0.f);
+                        if (post) t = fmaf(t, es2[q], et2[q]);
+                        y[q] = t;
+                    }
+                    *reinterpret_cast<float4 *>(a.out + m * a.N + nb) = make_float4(y[0], y[1], y[2], y[3]);
+                }
+            }
+        }
+        tc_fence_before();
+    } else {
+        // ============================ B loader + MMA issuer ============================
+        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+        auto issue_b = [&](int kb) {
+            if (kb < nkb) {
+                unsigned char *bh = b_ring + (kb % SB) * Cfg::B_STAGE, *bl = bh + Cfg::B_TILE;
+                const int k0 = kb * TBK;
+#pragma unroll
+                for (int i = 0; i < (BN * 8) / 32; ++i) {
+                    const int idx = lane + i * 32;
+                    const int n = idx >> 3, j = idx & 7;
+                    const int64_t g = (int64_t)(n0 + n) * a.Kp + k0 + 4 * j;
+                    const int off = n * 128 + ((j ^ (n & 7)) << 4);
+                    cp_async16(bh + off, a.wt_hi + g, 16);
+                    cp_async16(bl + off, a.wt_lo + g, 16);
+                }
+            }
+            cp_async_commit();
+        };
+#pragma unroll
+        for (int p = 0; p < SB - 2; ++p) issue_b(p);
+        for (int kb = 0; kb < nkb; ++kb) {
+            // refill the slot of k-block kb-2 (committed two iterations ago, so the MMAs of kb-1 may
+            // still be running: the tensor pipe is never drained) with k-block kb+SB-2
+            if (kb > 1) mbar_wait(&emptyB[(kb - 2) % SB], ((kb - 2) / SB) & 1);
+            issue_b(kb + SB - 2);
+            cp_async_wait<SB - 2>();
+            fence_proxy_async();
+            __syncwarp();
+            const int st = kb % ST;
+            mbar_wait(&fullA[st], (kb / ST) & 1);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t bs = smem_u32(b_ring + (kb % SB) * Cfg::B_STAGE);
+                const uint64_t dbh = make_sw128_desc(bs), dbl = make_sw128_desc(bs + Cfg::B_TILE);
+                const uint32_t d_main = tmem_base, d_lo = tmem_base + BN;
+#pragma unroll
+                for (int kk = 0; kk < TBK / 8; ++kk) {
+                    const uint32_t first = (kb > 0 || kk > 0) ? 1u : 0u;
+                    const uint32_t ta = tmem_base + Cfg::ACC_COLS + st * 2 * TBK + kk * 8;
+                    umma_tf32_ts(d_main, ta, dbh + 2 * kk, idesc, first);                 // Ah.Bh
+                    umma_tf32_ts(d_lo, ta, dbl + 2 * kk, idesc, first);                   // Ah.Bl
+                    umma_tf32_ts(d_lo, ta + TBK, dbh + 2 * kk, idesc, 1u);                // Al.Bh
+                }
+                umma_commit(&emptyA[st]);
+                umma_commit(&emptyB[kb % SB]);
+                if (kb == nkb - 1) umma_commit(accum);
+            }
+            __syncwarp();
+        }
+        cp_async_wait<0>();
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
+    }
+}
+
+template <int BN, int DA, int SB, int ST>
+int launch_tc2(const ConvArgs &a, cudaStream_t st)
+{
+    using Cfg = Tc2Cfg<BN, DA, SB, ST>;
+    auto kern = conv_gemm_tc2_kernel<BN, DA, SB, ST>;
+    static bool configured = false;
+    if (!configured) {
+        ISS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+        configured = true;
+    }
+    const int64_t gm = (a.M + TBM - 1) / TBM;
+    ISS_REQUIRE(gm < (1ll << 31), ISS_ERR_INVALID, "conv_tc: M too large");
+    dim3 grid((unsigned)gm, (unsigned)(a.N / BN));
+    kern<<<grid, 160, Cfg::SMEM, st>>>(a);
+    ISS_CUDA_OK(cudaGetLastError());
+    iss_count_launch();
+    return ISS_OK;
+}
+
 template <int BN, int STAGES, bool A_TMEM>
 int launch_tc(const ConvArgs &a, cudaStream_t st)
 {
@@ -422,9 +685,14 @@ int iss_launch_conv_tc(const ConvArgs &a, int mode, cudaStream_t st)
     const bool ts = (mode == ISS_GEMM_TC_TS);
     // BN: the widest of {256,128,64,32} dividing N
     // two accumulators per tile (main + correction) => BN <= 128 (2 x 128 + A ring <= 512 TMEM columns)
-    if (a.N % 128 == 0) return ts ? launch_tc<128, 3, true>(a, st) : launch_tc<128, 2, false>(a, st);
-    if (a.N % 64 == 0) return ts ? launch_tc<64, 2, true>(a, st) : launch_tc<64, 2, false>(a, st);
-    return ts ? launch_tc<32, 3, true>(a, st) : launch_tc<32, 3, false>(a, st);
+    if (ts) {
+        if (a.N % 128 == 0) return launch_tc2<128, 4, 4, 2>(a, st);      // 193 KB smem, 384 -> 512 TMEM cols, 1 CTA/SM
+        if (a.N % 64 == 0) return launch_tc2<64, 2, 4, 2>(a, st);        //  97 KB smem, 256 TMEM cols, 2 CTAs/SM
+        return launch_tc2<32, 3, 4, 3>(a, st);                            //  81 KB smem, 256 TMEM cols
+    }
+    if (a.N % 128 == 0) return launch_tc<128, 2, false>(a, st);
+    if (a.N % 64 == 0) return launch_tc<64, 2, false>(a, st);
+    return launch_tc<32, 3, false>(a, st);
 }
 
 // Host-side preparation of a layer's weights for the tensor-core path:
