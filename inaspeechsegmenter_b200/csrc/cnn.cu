@@ -352,7 +352,7 @@ extern "C" int iss_cnn_forward(iss_ctx *ctx, iss_cnn *cnn, const float *d_mspec,
                 a.post_scale = (d.flags & ISS_F_AFFINE_POST) ? blob + d.post_scale_off : nullptr;
                 a.post_shift = (d.flags & ISS_F_AFFINE_POST) ? blob + d.post_shift_off : nullptr;
                 a.out = dst;
-                if (Lr.d_wt) { a.wt_hi = Lr.d_wt; a.wt_lo = Lr.d_wt + (size_t)d.cout * Lr.Kp; a.Kp = Lr.Kp; }
+                if (Lr.d_wt) { a.wt_hi = Lr.d_wt; a.wt_lo = Lr.d_wt + (size_t)d.cout * Lr.Kp; a.wt_tiled = Lr.d_wt + 2 * (size_t)d.cout * Lr.Kp; a.Kp = Lr.Kp; }
                 a.flags = d.flags & ~ISS_F_SOFTMAX;
                 a.N = d.cout;
                 if (d.kind == ISS_LAYER_DENSE) {

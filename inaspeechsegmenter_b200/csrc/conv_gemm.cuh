@@ -21,7 +21,7 @@ struct ConvArgs {
     int ld;
     const int32_t *row0; const float *mu; const float *sigma;
     // tensor-core path: weights transposed + split, [N][Kp] each (nullptr => fp32 CUDA-core kernel)
-    const float *wt_hi; const float *wt_lo; int Kp;
+    const float *wt_hi; const float *wt_lo; const float *wt_tiled; int Kp;
 };
 
 #define ISS_GEMM_FP32  0      /* fp32 CUDA cores (conv_gemm.cu) */
@@ -34,7 +34,7 @@ struct ConvArgs {
 extern "C" int iss_get_gemm_mode(void);
 bool iss_conv_tc_eligible(const ConvArgs &a);
 int iss_launch_conv_tc(const ConvArgs &a, int mode, cudaStream_t st);
-// W[K][N] -> device buffer [2][N][Kp] (hi then lo), Kp = K rounded up to 32
+// W[K][N] -> device buffer: [2][N][Kp] row-major (hi, lo) then the tiled/pre-swizzled image [2*N*Kp]; Kp = K rounded up to 32
 int iss_prepare_tc_weights(const float *h_w, int K, int N, float **d_out, int *Kp_out);
 
 // Launches the layer on `st`.  first = gather from log-mel rows with (x - mu) / sigma.

@@ -409,8 +409,8 @@ conv_gemm_tc2_kernel(const ConvArgs a)
     unsigned char *b_ring = smem;                                        // 1024-aligned operand tiles first
     unsigned char *a_ring = smem + SB * Cfg::B_STAGE;
     uint64_t *bars = reinterpret_cast<uint64_t *>(a_ring + Cfg::A_RING);
-    uint64_t *fullA = bars, *emptyA = bars + ST, *emptyB = bars + 2 * ST, *accum = bars + 2 * ST + SB;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * ST + SB + 1);
+    uint64_t *fullA = bars, *emptyA = bars + ST, *emptyB = bars + 2 * ST, *fullB = bars + 2 * ST + SB, *accum = bars + 2 * ST + 2 * SB;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * ST + 2 * SB + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t m0 = (int64_t)blockIdx.x * TBM;
@@ -419,7 +419,7 @@ conv_gemm_tc2_kernel(const ConvArgs a)
 
     if (tid == 0) {
         for (int s = 0; s < ST; ++s) { mbar_init(&fullA[s], 128); mbar_init(&emptyA[s], 1); }
-        for (int s = 0; s < SB; ++s) mbar_init(&emptyB[s], 1);
+        for (int s = 0; s < SB; ++s) { mbar_init(&emptyB[s], 1); mbar_init(&fullB[s], 1); }
         mbar_init(accum, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -555,41 +555,32 @@ conv_gemm_tc2_kernel(const ConvArgs a)
         }
         tc_fence_before();
     } else {
-        // ============================ B loader + MMA issuer ============================
+        // ============================ B loader + MMA issuer (one thread) ============================
+        // The weights are static, so the host stores them already tiled and swizzled exactly as the
+        // smem operand image ([n-tile][k-block][hi|lo][BN x 128 B, SWIZZLE_128B]); one stage is then a
+        // single 1-D bulk copy (async proxy, completes on an mbarrier) instead of BN*16 cp.async.
         constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
-        auto issue_b = [&](int kb) {
-            if (kb < nkb) {
-                unsigned char *bh = b_ring + (kb % SB) * Cfg::B_STAGE, *bl = bh + Cfg::B_TILE;
-                const int k0 = kb * TBK;
-#pragma unroll
-                for (int i = 0; i < (BN * 8) / 32; ++i) {
-                    const int idx = lane + i * 32;
-                    const int n = idx >> 3, j = idx & 7;
-                    const int64_t g = (int64_t)(n0 + n) * a.Kp + k0 + 4 * j;
-                    const int off = n * 128 + ((j ^ (n & 7)) << 4);
-                    cp_async16(bh + off, a.wt_hi + g, 16);
-                    cp_async16(bl + off, a.wt_lo + g, 16);
+        if (lane == 0) {
+            const unsigned char *wt = reinterpret_cast<const unsigned char *>(a.wt_tiled) +
+                                      (size_t)blockIdx.y * nkb * Cfg::B_STAGE;
+            auto issue_b = [&](int kb) {
+                if (kb < nkb) {
+                    const int sl = kb % SB;
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&fullB[sl])), "r"((uint32_t)Cfg::B_STAGE) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(smem_u32(b_ring + sl * Cfg::B_STAGE)), "l"(wt + (size_t)kb * Cfg::B_STAGE),
+                                   "r"((uint32_t)Cfg::B_STAGE), "r"(smem_u32(&fullB[sl])) : "memory");
                 }
-            }
-            cp_async_commit();
-        };
-#pragma unroll
-        for (int p = 0; p < SB - 2; ++p) issue_b(p);
-        for (int kb = 0; kb < nkb; ++kb) {
-            // refill the slot of k-block kb-2 (committed two iterations ago, so the MMAs of kb-1 may
-            // still be running: the tensor pipe is never drained) with k-block kb+SB-2
-            if (kb > 1) mbar_wait(&emptyB[(kb - 2) % SB], ((kb - 2) / SB) & 1);
-            issue_b(kb + SB - 2);
-            cp_async_wait<SB - 2>();
-            fence_proxy_async();
-            __syncwarp();
-            const int st = kb % ST;
-            mbar_wait(&fullA[st], (kb / ST) & 1);
-            tc_fence_after();
-            if (lane == 0) {
-                const uint32_t bs = smem_u32(b_ring + (kb % SB) * Cfg::B_STAGE);
+            };
+            for (int p = 0; p < SB - 1; ++p) issue_b(p);
+            const uint32_t d_main = tmem_base, d_lo = tmem_base + BN;
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int st = kb % ST, sl = kb % SB;
+                mbar_wait(&fullB[sl], (kb / SB) & 1);
+                mbar_wait(&fullA[st], (kb / ST) & 1);
+                tc_fence_after();
+                const uint32_t bs = smem_u32(b_ring + sl * Cfg::B_STAGE);
                 const uint64_t dbh = make_sw128_desc(bs), dbl = make_sw128_desc(bs + Cfg::B_TILE);
-                const uint32_t d_main = tmem_base, d_lo = tmem_base + BN;
 #pragma unroll
                 for (int kk = 0; kk < TBK / 8; ++kk) {
                     const uint32_t first = (kb > 0 || kk > 0) ? 1u : 0u;
@@ -599,12 +590,17 @@ conv_gemm_tc2_kernel(const ConvArgs a)
                     umma_tf32_ts(d_lo, ta + TBK, dbh + 2 * kk, idesc, 1u);                // Al.Bh
                 }
                 umma_commit(&emptyA[st]);
-                umma_commit(&emptyB[kb % SB]);
+                umma_commit(&emptyB[sl]);
                 if (kb == nkb - 1) umma_commit(accum);
+                // refill the slot of k-block kb-1 with kb+SB-1: its MMAs retire before those just
+                // issued start, so this wait is short and the tensor pipe is never drained
+                if (kb >= 1 && kb + SB - 1 < nkb) {
+                    mbar_wait(&emptyB[(kb - 1) % SB], ((kb - 1) / SB) & 1);
+                    issue_b(kb + SB - 1);
+                }
             }
-            __syncwarp();
         }
-        cp_async_wait<0>();
+        __syncwarp();
         tc_fence_before();
     }
     __syncthreads();
@@ -677,7 +673,7 @@ extern "C" int iss_get_gemm_mode(void)
 
 bool iss_conv_tc_eligible(const ConvArgs &a)
 {
-    return a.wt_hi && a.wt_lo && a.Kp > 0 && a.C % 32 == 0 && a.K % 32 == 0 && a.N % 32 == 0 && a.N >= 32;
+    return a.wt_hi && a.wt_lo && a.wt_tiled && a.Kp > 0 && a.C % 32 == 0 && a.K % 32 == 0 && a.N % 32 == 0 && a.N >= 32;
 }
 
 int iss_launch_conv_tc(const ConvArgs &a, int mode, cudaStream_t st)
@@ -687,7 +683,7 @@ int iss_launch_conv_tc(const ConvArgs &a, int mode, cudaStream_t st)
     // two accumulators per tile (main + correction) => BN <= 128 (2 x 128 + A ring <= 512 TMEM columns)
     if (ts) {
         if (a.N % 128 == 0) return launch_tc2<128, 4, 4, 2>(a, st);      // 193 KB smem, 384 -> 512 TMEM cols, 1 CTA/SM
-        if (a.N % 64 == 0) return launch_tc2<64, 2, 4, 2>(a, st);        //  97 KB smem, 256 TMEM cols, 2 CTAs/SM
+        if (a.N % 64 == 0) return launch_tc2<64, 3, 3, 2>(a, st);        //  97 KB smem, 256 TMEM cols, 2 CTAs/SM
         return launch_tc2<32, 3, 4, 3>(a, st);                            //  81 KB smem, 256 TMEM cols
     }
     if (a.N % 128 == 0) return launch_tc<128, 2, false>(a, st);
@@ -695,13 +691,20 @@ int iss_launch_conv_tc(const ConvArgs &a, int mode, cudaStream_t st)
     return launch_tc<32, 3, false>(a, st);
 }
 
+static int tc_block_n(int N) { return N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 32); }
+
 // Host-side preparation of a layer's weights for the tensor-core path:
-// W[K][N] (Keras / our blob layout) -> transposed, zero-padded, split [2][N][Kp].
+// W[K][N] (Keras / our blob layout) ->
+//   (1) transposed, zero-padded, split row-major [2][N][Kp]           (SS kernel), followed by
+//   (2) the same values tiled and pre-swizzled as smem operand images
+//       [N/BN][Kp/32][hi|lo][BN rows x 128 B, 16-byte chunk j of row n stored at chunk j ^ (n & 7)]
+//       (TS kernel: one bulk copy per stage).
 int iss_prepare_tc_weights(const float *h_w, int K, int N, float **d_out, int *Kp_out)
 {
     const int Kp = (K + TBK - 1) / TBK * TBK;
-    std::vector<float> buf((size_t)2 * N * Kp, 0.f);
-    float *hi = buf.data(), *lo = buf.data() + (size_t)N * Kp;
+    const size_t plane = (size_t)N * Kp;
+    std::vector<float> buf(4 * plane, 0.f);
+    float *hi = buf.data(), *lo = buf.data() + plane, *tiled = buf.data() + 2 * plane;
     for (int k = 0; k < K; ++k)
         for (int n = 0; n < N; ++n) {
             const float w = h_w[(size_t)k * N + n];
@@ -713,6 +716,18 @@ int iss_prepare_tc_weights(const float *h_w, int K, int N, float **d_out, int *K
             hi[(size_t)n * Kp + k] = h;
             lo[(size_t)n * Kp + k] = w - h;
         }
+    const int BN = tc_block_n(N), nkb = Kp / TBK;
+    for (int nt = 0; nt < N / BN; ++nt)
+        for (int kb = 0; kb < nkb; ++kb)
+            for (int part = 0; part < 2; ++part) {
+                float *dst = tiled + (((size_t)nt * nkb + kb) * 2 + part) * (size_t)BN * TBK;
+                const float *src = part ? lo : hi;
+                for (int n = 0; n < BN; ++n)
+                    for (int k = 0; k < TBK; ++k) {
+                        const int chunk = (k >> 2) ^ (n & 7);
+                        dst[n * TBK + chunk * 4 + (k & 3)] = src[(size_t)(nt * BN + n) * Kp + kb * TBK + k];
+                    }
+            }
     float *d = nullptr;
     cudaError_t e = cudaMalloc(&d, buf.size() * sizeof(float));
     if (e != cudaSuccess) { iss_set_error("cudaMalloc tc weights: %s", cudaGetErrorString(e)); return ISS_ERR_NOMEM; }

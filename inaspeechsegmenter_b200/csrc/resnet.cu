@@ -269,7 +269,7 @@ extern "C" int iss_resnet_embed(iss_ctx *ctx, iss_resnet *net, const float *d_fe
         ConvArgs a = {};
         a.in = in; a.w = blob + c.w_off; a.pre_scale = blob + c.scale_off; a.pre_shift = blob + c.shift_off;
         a.residual = residual; a.out = out;
-        if (c.d_wt) { a.wt_hi = c.d_wt; a.wt_lo = c.d_wt + (size_t)c.cout * c.Kp; a.Kp = c.Kp; }
+        if (c.d_wt) { a.wt_hi = c.d_wt; a.wt_lo = c.d_wt + (size_t)c.cout * c.Kp; a.wt_tiled = c.d_wt + 2 * (size_t)c.cout * c.Kp; a.Kp = c.Kp; }
         a.M = (int64_t)nb * oh * ow; a.N = c.cout; a.K = c.kh * c.kw * c.cin;
         a.H = h; a.W = w; a.C = c.cin; a.OH = oh; a.OW = ow;
         a.KH = c.kh; a.KW = c.kw; a.SH = c.stride; a.SW = c.stride; a.PT = c.pad; a.PL = c.pad;
@@ -307,7 +307,7 @@ extern "C" int iss_resnet_embed(iss_ctx *ctx, iss_resnet *net, const float *d_fe
         a.M = nb; a.N = net->embed_dim; a.K = 2 * net->c_final * h;
         a.H = 1; a.W = 1; a.C = a.K; a.OH = 1; a.OW = 1; a.KH = 1; a.KW = 1; a.SH = 1; a.SW = 1;
         a.flags = ISS_F_BIAS;
-        if (net->d_emb_wt) { a.wt_hi = net->d_emb_wt; a.wt_lo = net->d_emb_wt + (size_t)net->embed_dim * net->emb_Kp; a.Kp = net->emb_Kp; }
+        if (net->d_emb_wt) { a.wt_hi = net->d_emb_wt; a.wt_lo = net->d_emb_wt + (size_t)net->embed_dim * net->emb_Kp; a.wt_tiled = net->d_emb_wt + 2 * (size_t)net->embed_dim * net->emb_Kp; a.Kp = net->emb_Kp; }
         rc = iss_launch_conv(a, false, st);
         if (rc != ISS_OK) return rc;
     }
