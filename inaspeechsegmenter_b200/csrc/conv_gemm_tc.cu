@@ -594,8 +594,8 @@ conv_gemm_tc2_kernel(const ConvArgs a)
                 if (kb == nkb - 1) umma_commit(accum);
                 // refill the slot of k-block kb-1 with kb+SB-1: its MMAs retire before those just
                 // issued start, so this wait is short and the tensor pipe is never drained
-                if (kb >= 1 && kb + SB - 1 < nkb) {
-                    mbar_wait(&emptyB[(kb - 1) % SB], ((kb - 1) / SB) & 1);
+                if (kb + SB - 1 < nkb) {
+                    if (kb >= 1) mbar_wait(&emptyB[(kb - 1) % SB], ((kb - 1) / SB) & 1);   // slot (kb-1)%SB; unused so far when kb == 0
                     issue_b(kb + SB - 1);
                 }
             }
