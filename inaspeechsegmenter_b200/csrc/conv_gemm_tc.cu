@@ -45,17 +45,30 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
 {
+    uint32_t ok;
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a pipeline bug must surface as an error (trap), never as a hung GPU.
+__device__ __noinline__ void mbar_timeout(int tag, uint32_t parity)
+{
+    printf("libiss_b200: mbarrier wait timed out (tag %d, parity %u, block %d,%d, thread %d)\n", tag, parity,
+           (int)blockIdx.x, (int)blockIdx.y, (int)threadIdx.x);
+    __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int tag = 0)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity))
+        if (clock64() - t0 > 4000000000ll) mbar_timeout(tag, parity);      // ~2 s at 1.9 GHz
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -487,7 +500,7 @@ conv_gemm_tc2_kernel(const ConvArgs a)
 #pragma unroll
             for (int j = 0; j < 32; ++j) hi[j] = v[j] & 0xFFFFE000u;
             const int st = kb % ST;
-            mbar_wait(&emptyA[st], ((kb / ST) & 1) ^ 1);
+            mbar_wait(&emptyA[st], ((kb / ST) & 1) ^ 1, 1);
             tc_fence_after();
             const uint32_t ta = tmem_base + lane_addr + Cfg::ACC_COLS + st * 2 * TBK;
             tmem_st32(ta, hi);
@@ -501,7 +514,7 @@ conv_gemm_tc2_kernel(const ConvArgs a)
         cp_async_wait<0>();
 
         // ============================ epilogue ============================
-        mbar_wait(accum, 0);
+        mbar_wait(accum, 0, 5);
         tc_fence_after();
         unsigned char *stage_buf = my_ring;                  // the A ring is idle now: reuse slot 0 as transpose buffer
         const bool has_bias = a.flags & ISS_F_BIAS, pre = a.flags & ISS_F_AFFINE_PRE, post = a.flags & ISS_F_AFFINE_POST;
@@ -576,8 +589,8 @@ conv_gemm_tc2_kernel(const ConvArgs a)
             const uint32_t d_main = tmem_base, d_lo = tmem_base + BN;
             for (int kb = 0; kb < nkb; ++kb) {
                 const int st = kb % ST, sl = kb % SB;
-                mbar_wait(&fullB[sl], (kb / SB) & 1);
-                mbar_wait(&fullA[st], (kb / ST) & 1);
+                mbar_wait(&fullB[sl], (kb / SB) & 1, 2);
+                mbar_wait(&fullA[st], (kb / ST) & 1, 3);
                 tc_fence_after();
                 const uint32_t bs = smem_u32(b_ring + sl * Cfg::B_STAGE);
                 const uint64_t dbh = make_sw128_desc(bs), dbl = make_sw128_desc(bs + Cfg::B_TILE);
@@ -595,7 +608,7 @@ conv_gemm_tc2_kernel(const ConvArgs a)
                 // refill the slot of k-block kb-1 with kb+SB-1: its MMAs retire before those just
                 // issued start, so this wait is short and the tensor pipe is never drained
                 if (kb + SB - 1 < nkb) {
-                    if (kb >= 1) mbar_wait(&emptyB[(kb - 1) % SB], ((kb - 1) / SB) & 1);   // slot (kb-1)%SB; unused so far when kb == 0
+                    if (kb >= 1) mbar_wait(&emptyB[(kb - 1) % SB], ((kb - 1) / SB) & 1, 4);   // slot (kb-1)%SB; unused so far when kb == 0
                     issue_b(kb + SB - 1);
                 }
             }
