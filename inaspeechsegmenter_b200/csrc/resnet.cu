@@ -146,7 +146,7 @@ int64_t max_act_per_window(const iss_resnet *net, int T, double *flops)
     return mx;
 }
 
-constexpr int RES_BATCH = 32;          // windows per sweep
+constexpr int RES_BATCH = 128;         // windows per sweep (layer4 then still has 128*8*18/128 = 144 M-tiles)
 
 }  // namespace
 

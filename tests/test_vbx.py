@@ -58,6 +58,11 @@ def test_resnet_blob_layout():
 gpu = pytest.mark.gpu
 
 
+def _lib_mod():
+    from inaspeechsegmenter_b200 import _lib
+    return _lib
+
+
 @pytest.fixture(scope='module')
 def vctx():
     if not torch.cuda.is_available():
@@ -100,11 +105,21 @@ def test_k5_resnet_vs_oracle(vctx, golden):
     assert abs(ext.flops_per_window - 11.30e9) < 0.05e9       # 5.65 GMAC per 64x144 window
     x, y = golden['resnet_x'], golden['resnet_y']              # produced by the REAL resnet.py
     scale = np.abs(y).max()
-    for i in range(len(x)):
-        got = ext.get_embedding(x[i].T)                        # get_embedding takes [T, 64]
-        assert np.abs(got - y[i]).max() <= 2e-4 * scale, np.abs(got - y[i]).max() / scale
-    got = ext.get_embedding(golden['resnet_xs'][0].T)          # tail-window length 131
-    assert np.abs(got - golden['resnet_ys'][0]).max() <= 2e-4 * np.abs(golden['resnet_ys']).max()
+    lib = _lib_mod().load()
+    prev = lib.iss_get_gemm_mode()
+    # tolerance relative to max|y| after 104 convolution layers: fp32 CUDA-core engine 2e-5;
+    # tcgen05 3xTF32 engines 2e-4 (tensor-core accumulation truncates; measured 7.5e-5).  The
+    # reference's own check of this network is 4 decimals (run_test.py:189-195).
+    try:
+        for mode, tol in ((0, 2e-5), (1, 2e-4), (2, 2e-4)):
+            lib.iss_set_gemm_mode(mode)
+            for i in range(len(x)):
+                got = ext.get_embedding(x[i].T)                    # get_embedding takes [T, 64]
+                assert np.abs(got - y[i]).max() <= tol * scale, (mode, np.abs(got - y[i]).max() / scale)
+            got = ext.get_embedding(golden['resnet_xs'][0].T)      # tail-window length 131
+            assert np.abs(got - golden['resnet_ys'][0]).max() <= tol * np.abs(golden['resnet_ys']).max(), mode
+    finally:
+        lib.iss_set_gemm_mode(prev)
 
 
 @gpu
