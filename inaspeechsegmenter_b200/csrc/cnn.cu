@@ -105,6 +105,97 @@ patch_stats_kernel(const float *__restrict__ mspec, int ld, int w, int64_t n, Pa
     }
 }
 
+// ------------------------------------------------------------------ first layer: direct conv on the z-normalised patch
+// The first Conv2D has one input channel (K = kh*kw ~ 20), far too thin for a GEMM tile.  One CTA
+// stages a whole patch in shared memory, normalising each log-mel value exactly once with the
+// reference's arithmetic ((x - mean) / std in float32, segmenter.py:82), zero-padded for 'same'
+// convolutions; a thread owns 4 output channels x 4 consecutive output columns, so a filter tap is
+// one LDS.128 (weights) + 4 broadcast LDS.32 (inputs) for 16 FMAs.  Taps are accumulated in the
+// same (kh, kw) order as the implicit-GEMM kernel, so both produce identical bits.
+struct FirstArgs {
+    const float *mspec; int ld;
+    const int32_t *row0; const float *mu; const float *sigma;
+    const float *w, *bias, *pre_scale, *pre_shift, *post_scale, *post_shift;
+    float *out;
+    int64_t n;
+    int H, W, OH, OW, KH, KW, SH, SW, PT, PL, Hp, Wp, Cout, flags;
+};
+
+constexpr int FIRST_P = 4;
+
+__global__ void __launch_bounds__(256)
+conv_first_direct_kernel(const FirstArgs a)
+{
+    extern __shared__ __align__(16) float fsm[];
+    float *ws = fsm;                                   // [K][Cout]
+    float *xs = fsm + a.KH * a.KW * a.Cout;            // [Hp][Wp] (+ slack), zero border
+    const int tid = threadIdx.x;
+    const int CQ = a.Cout >> 2, streams = 256 / CQ;
+    const int c4 = tid % CQ, stream = tid / CQ;
+    const int K = a.KH * a.KW;
+    for (int i = tid; i < K * a.Cout; i += 256) ws[i] = a.w[i];
+    const int xs_len = a.Hp * a.Wp + FIRST_P * a.SW + a.KW;
+    float eb[4], es1[4], et1[4], es2[4], et2[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int c = c4 * 4 + q;
+        eb[q] = (a.flags & ISS_F_BIAS) ? a.bias[c] : 0.f;
+        es1[q] = (a.flags & ISS_F_AFFINE_PRE) ? a.pre_scale[c] : 1.f;  et1[q] = (a.flags & ISS_F_AFFINE_PRE) ? a.pre_shift[c] : 0.f;
+        es2[q] = (a.flags & ISS_F_AFFINE_POST) ? a.post_scale[c] : 1.f; et2[q] = (a.flags & ISS_F_AFFINE_POST) ? a.post_shift[c] : 0.f;
+    }
+    const int nblk = (a.OW + FIRST_P - 1) / FIRST_P;
+    const int G = a.OH * nblk;
+    for (int64_t img = blockIdx.x; img < a.n; img += gridDim.x) {
+        __syncthreads();                               // previous patch fully consumed (and ws visible)
+        for (int i = tid; i < xs_len; i += 256) xs[i] = 0.f;
+        __syncthreads();
+        const float mu = a.mu[img], sg = a.sigma[img];
+        const float *src = a.mspec + (int64_t)a.row0[img] * a.ld;
+        for (int e = tid; e < a.H * a.W; e += 256) {
+            const int r = e / a.W, c = e - r * a.W;
+            xs[(r + a.PT) * a.Wp + c + a.PL] = __fdiv_rn(__fsub_rn(__ldg(src + (int64_t)r * a.ld + c), mu), sg);
+        }
+        __syncthreads();
+        float *out_img = a.out + img * ((int64_t)a.OH * a.OW * a.Cout);
+        for (int g = stream; g < G; g += streams) {
+            const int oh = g / nblk, ow0 = (g - oh * nblk) * FIRST_P;
+            float acc[FIRST_P][4];
+#pragma unroll
+            for (int p = 0; p < FIRST_P; ++p)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[p][q] = 0.f;
+            for (int r = 0; r < a.KH; ++r) {
+                const float *xrow = xs + (oh * a.SH + r) * a.Wp + ow0 * a.SW;
+                const float *wrow = ws + (r * a.KW) * a.Cout + c4 * 4;
+                for (int t = 0; t < a.KW; ++t) {
+                    const float4 w4 = *reinterpret_cast<const float4 *>(wrow + t * a.Cout);
+#pragma unroll
+                    for (int p = 0; p < FIRST_P; ++p) {
+                        const float x = xrow[p * a.SW + t];
+                        acc[p][0] = fmaf(x, w4.x, acc[p][0]); acc[p][1] = fmaf(x, w4.y, acc[p][1]);
+                        acc[p][2] = fmaf(x, w4.z, acc[p][2]); acc[p][3] = fmaf(x, w4.w, acc[p][3]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < FIRST_P; ++p) {
+                if (ow0 + p >= a.OW) continue;
+                float y[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float v = acc[p][q] + eb[q];
+                    if (a.flags & ISS_F_AFFINE_PRE) v = fmaf(v, es1[q], et1[q]);
+                    if (a.flags & ISS_F_RELU) v = fmaxf(v, 0.f);
+                    if (a.flags & ISS_F_SIGMOID) v = 1.f / (1.f + expf(-v));
+                    if (a.flags & ISS_F_AFFINE_POST) v = fmaf(v, es2[q], et2[q]);
+                    y[q] = v;
+                }
+                *reinterpret_cast<float4 *>(out_img + ((int64_t)oh * a.OW + ow0 + p) * a.Cout + c4 * 4) = make_float4(y[0], y[1], y[2], y[3]);
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------ max pooling (NHWC)
 __global__ void __launch_bounds__(256)
 maxpool_nhwc_kernel(const float *__restrict__ in, float *__restrict__ out, int64_t total, int H, int W, int C,
@@ -366,8 +457,33 @@ extern "C" int iss_cnn_forward(iss_ctx *ctx, iss_cnn *cnn, const float *d_mspec,
                 int rc;
                 if (li == 0) {
                     ISS_REQUIRE(d.kind == ISS_LAYER_CONV2D, ISS_ERR_UNSUPPORTED, "iss_cnn_forward: first layer must be Conv2D");
-                    a.in = d_mspec; a.ld = ld; a.row0 = pa.row0 + b0; a.mu = pa.mu + b0; a.sigma = pa.sigma + b0;
-                    rc = iss_launch_conv(a, true, st);
+                    const bool direct = d.cin == 1 && (d.cout == 16 || d.cout == 32 || d.cout == 64 || d.cout == 128) &&
+                                        !(d.flags & ISS_F_SOFTMAX);
+                    if (direct) {
+                        FirstArgs f = {};
+                        f.mspec = d_mspec; f.ld = ld; f.row0 = pa.row0 + b0; f.mu = pa.mu + b0; f.sigma = pa.sigma + b0;
+                        f.w = a.w; f.bias = a.bias; f.pre_scale = a.pre_scale; f.pre_shift = a.pre_shift;
+                        f.post_scale = a.post_scale; f.post_shift = a.post_shift; f.out = dst; f.n = nb;
+                        f.H = Lr.in_h; f.W = Lr.in_w; f.OH = Lr.out_h; f.OW = Lr.out_w; f.KH = d.kh; f.KW = d.kw;
+                        f.SH = d.sh; f.SW = d.sw; f.PT = d.pad_top; f.PL = d.pad_left;
+                        f.Hp = Lr.in_h + d.pad_top + d.pad_bottom; f.Wp = Lr.in_w + d.pad_left + d.pad_right;
+                        f.Cout = d.cout; f.flags = a.flags;
+                        const size_t smem = ((size_t)d.kh * d.kw * d.cout + (size_t)f.Hp * f.Wp + FIRST_P * d.sw + d.kw + 8) * sizeof(float);
+                        ISS_REQUIRE(smem <= 200 * 1024, ISS_ERR_UNSUPPORTED, "iss_cnn_forward: first layer too large for the direct kernel");
+                        static bool configured = false;
+                        if (!configured) {
+                            ISS_CUDA_OK(cudaFuncSetAttribute(conv_first_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                            configured = true;
+                        }
+                        const unsigned grid = (unsigned)std::min<int64_t>(nb, (int64_t)ctx->sm_count * 8);
+                        conv_first_direct_kernel<<<grid, 256, smem, st>>>(f);
+                        ISS_CUDA_OK(cudaGetLastError());
+                        iss_count_launch();
+                        rc = ISS_OK;
+                    } else {
+                        a.in = d_mspec; a.ld = ld; a.row0 = pa.row0 + b0; a.mu = pa.mu + b0; a.sigma = pa.sigma + b0;
+                        rc = iss_launch_conv(a, true, st);
+                    }
                 } else {
                     a.in = cur;
                     rc = iss_launch_conv(a, false, st);
