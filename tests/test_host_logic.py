@@ -135,3 +135,37 @@ def test_segmenter_fails_loudly_without_gpu():
     from inaspeechsegmenter_b200 import Segmenter
     with pytest.raises(_lib.IssError):
         Segmenter(ffmpeg=None, models={})
+
+
+def test_hdf5_reader_on_reference_fixture(media):
+    """The pure-Python reader parses the reference's genuine h5py-written media/test.h5
+    (the fixture of run_test.py:189-195) and finds both datasets at the offsets SURVEY section 4 lists."""
+    from inaspeechsegmenter_b200 import keras_hdf5 as kh
+    path = os.path.join(media, 'test.h5')
+    f = kh.H5File(path)
+    mel, emb = f.read_dataset(f.get('lamartinemelbands')), f.read_dataset(f.get('lamartineonnx'))
+    raw = open(path, 'rb').read()
+    assert mel.shape == (144, 64) and emb.shape == (256,) and mel.dtype == np.float32
+    assert np.array_equal(mel, np.frombuffer(raw[2048:2048 + 144 * 64 * 4], '<f4').reshape(144, 64))
+    assert np.array_equal(emb, np.frombuffer(raw[40960:40960 + 1024], '<f4'))
+
+
+def test_keras_hdf5_roundtrip_and_model_lookup(tmp_path, synth_models, monkeypatch):
+    from inaspeechsegmenter_b200 import keras_hdf5 as kh
+    cfg, w = synth_models['gender']
+    p = tmp_path / 'keras_male_female_cnn.hdf5'
+    kh.write_keras_hdf5(str(p), cfg, w)
+    cfg2, w2 = kh.load_keras_hdf5(str(p))
+    assert cfg2 == cfg and set(w2) == set(w) and all(np.array_equal(w[k], w2[k]) for k in w)
+    monkeypatch.setenv(models.MODEL_DIR_ENV, str(tmp_path))
+    assert models.find_model_file('keras_male_female_cnn.hdf5') == str(p)
+    cfg3, w3 = models.load_model_file(models.find_model_file('keras_male_female_cnn.hdf5'))
+    low = models.lower_keras_model(cfg3, w3, 68, 24)
+    assert low.n_classes == 2 and len(low.descs) == 9
+    assert models.find_model_file('keras_speech_music_cnn.hdf5') is None
+
+
+def test_cli_parser_matches_reference_flags():
+    from inaspeechsegmenter_b200 import cli
+    a = cli.build_parser().parse_args(['-i', 'x.wav', '-o', '/tmp', '-d', 'sm', '-g', 'false', '-b', 'None', '-e', 'textgrid', '-r', '0.05', '-s', '1024'])
+    assert (a.vad_engine, a.detect_gender, a.ffmpeg_binary, a.export_format, a.energy_ratio, a.batch_size) == ('sm', 'false', 'None', 'textgrid', 0.05, 1024)
