@@ -83,12 +83,10 @@ viterbi_forward_kernel(const float *__restrict__ src, const double *__restrict__
         }
         const int nstep = (int)min((int64_t)32, T - base);
         unsigned mybp = 0;
-        for (int s = 0; s < nstep; ++s) {
-            double es[K];
-#pragma unroll
-            for (int j = 0; j < K; ++j) es[j] = __shfl_sync(0xffffffffu, e[j], s);
+        // one DP step on emissions `es`; `is_first` only for the very first step of the sequence
+        auto dp_step = [&](const double (&es)[K], bool is_first) -> unsigned {
             unsigned bp = 0;
-            if (base + s == 0) {
+            if (is_first) {
 #pragma unroll
                 for (int j = 0; j < K; ++j) { V[j] = es[j] + prm.prior; bp |= (unsigned)j << (2 * j); }
             } else {
@@ -113,7 +111,27 @@ viterbi_forward_kernel(const float *__restrict__ src, const double *__restrict__
 #pragma unroll
                 for (int j = 0; j < K; ++j) V[j] = Vn[j];
             }
-            if (lane == s) mybp = bp;
+            return bp;
+        };
+        if (nstep == 32 && base > 0) {
+            // full block, fully unrolled: the 32 x K emission shuffles do not depend on V, so they are
+            // issued ahead and only the add/compare/select chain remains on the serial critical path
+#pragma unroll
+            for (int s = 0; s < 32; ++s) {
+                double es[K];
+#pragma unroll
+                for (int j = 0; j < K; ++j) es[j] = __shfl_sync(0xffffffffu, e[j], s);
+                const unsigned bp = dp_step(es, false);
+                mybp = (lane == s) ? bp : mybp;
+            }
+        } else {
+            for (int s = 0; s < nstep; ++s) {
+                double es[K];
+#pragma unroll
+                for (int j = 0; j < K; ++j) es[j] = __shfl_sync(0xffffffffu, e[j], s);
+                const unsigned bp = dp_step(es, base + s == 0);
+                if (lane == s) mybp = bp;
+            }
         }
         if (t < T) lay.bp[t0 + t] = (uint8_t)mybp;
     }

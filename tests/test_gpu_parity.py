@@ -297,3 +297,21 @@ def test_e2e_short_media(rt, synth_models):
         got = seg.segment_signal(s16)
         ref, _, _ = _oracle_segmentation(s16.astype(np.float32) / np.float32(32768), synth_models, 'sm', True)
     assert got == ref
+
+
+def test_cli_with_hdf5_models(rt, synth_models, media, tmp_path, monkeypatch):
+    """CLI (reference flags) + Keras .hdf5 model lookup: models are read through the pure-Python
+    HDF5 reader from $ISS_B200_MODEL_DIR, outputs are the reference's CSV format."""
+    from inaspeechsegmenter_b200 import cli, keras_hdf5, models as M
+    mdir = tmp_path / 'models'
+    mdir.mkdir()
+    keras_hdf5.write_keras_hdf5(str(mdir / 'keras_speech_music_noise_cnn.hdf5'), *synth_models['smn'])
+    keras_hdf5.write_keras_hdf5(str(mdir / 'keras_male_female_cnn.hdf5'), *synth_models['gender'])
+    monkeypatch.setenv(M.MODEL_DIR_ENV, str(mdir))
+    out = tmp_path / 'out'
+    out.mkdir()
+    cli.main(['-i', os.path.join(media, 'silence2sec.wav'), os.path.join(media, 'musanmix.wav'), '-o', str(out), '-b', 'None'])
+    assert (out / 'silence2sec.csv').read_bytes() == open(os.path.join(media, 'silence2sec-smn-gender.csv'), 'rb').read()
+    got = (out / 'musanmix.csv').read_text().splitlines()
+    ref = open(os.path.join(media, 'musanmix-smn-gender.csv')).read().splitlines()
+    assert got[0] == ref[0] and [l for l in got if l.startswith('noEnergy')] == [l for l in ref if l.startswith('noEnergy')]
