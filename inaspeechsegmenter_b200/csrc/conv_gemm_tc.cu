@@ -447,44 +447,64 @@ conv_gemm_tc2_kernel(const ConvArgs a)
 
     if (warp < 4) {
         // ============================ A producers ============================
+        // Issue-slot budget matters here (the kernel is instruction-issue bound before it is tensor
+        // bound): per-row state is 32-bit and precomputed, the filter tap advances incrementally
+        // (no integer division in the loop) and un-padded convolutions skip all bounds checks.
         const int sub = lane >> 3, chunk = lane & 7;
-        int64_t row_off[8];
+        uint32_t row_base[8];                                // element offset of (img, ih0, iw0) + chunk*4 (wraps for padded rows)
         int row_ih0[8], row_iw0[8];
-        bool row_ok[8];
+        uint32_t row_dst[8];                                 // swizzled byte offset inside a ring slot
+        uint32_t ok_mask = 0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int64_t m = m0 + warp * 32 + 4 * i + sub;
-            row_ok[i] = m < a.M;
-            const int64_t mm = row_ok[i] ? m : 0;
+            const bool okr = m < a.M;
+            ok_mask |= (okr ? 1u : 0u) << i;
+            const int64_t mm = okr ? m : 0;
             const int ohw = a.OH * a.OW;
             const int64_t img = mm / ohw;
             const int rem = (int)(mm - img * ohw);
             const int oh = rem / a.OW, ow = rem - oh * a.OW;
             row_ih0[i] = oh * a.SH - a.PT; row_iw0[i] = ow * a.SW - a.PL;
-            row_off[i] = img * ((int64_t)a.H * a.W * a.C) + ((int64_t)row_ih0[i] * a.W + row_iw0[i]) * a.C;
+            row_base[i] = (uint32_t)(img * ((int64_t)a.H * a.W * a.C) + ((int64_t)row_ih0[i] * a.W + row_iw0[i]) * a.C + chunk * 4);
+            const int rl = 4 * i + sub;
+            row_dst[i] = (uint32_t)(rl * 128 + ((chunk ^ (rl & 7)) << 4));
         }
+        const bool padded = (a.PT | a.PL) != 0 || (a.OH - 1) * a.SH + a.KH > a.H || (a.OW - 1) * a.SW + a.KW > a.W;
         unsigned char *my_ring = a_ring + warp * DA * Cfg::A_SLOT;
-        auto issue_a = [&](int kb) {
-            if (kb < nkb) {
-                const int k0 = kb * TBK;
-                const int tap = k0 / a.C, c0 = k0 - tap * a.C;
-                const int rr = tap / a.KW, ss = tap - rr * a.KW;
-                const int64_t tap_off = ((int64_t)rr * a.W + ss) * a.C + c0 + chunk * 4;
-                unsigned char *slot = my_ring + (kb % DA) * Cfg::A_SLOT;
+        const uint32_t ring_u32 = smem_u32(my_ring);
+        // incremental tap state of the NEXT k-block to issue
+        int is_c0 = 0, is_ss = 0, is_rr = 0, is_kb = 0;
+        uint32_t is_off = 0;                                 // (rr*W + ss)*C + c0
+        const uint32_t wrap_step = (uint32_t)((a.W - a.KW) * a.C + TBK);
+        auto issue_a = [&]() {
+            if (is_kb < nkb) {
+                const uint32_t slot = ring_u32 + (uint32_t)(is_kb % DA) * Cfg::A_SLOT;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const int ih = row_ih0[i] + rr, iw = row_iw0[i] + ss;
-                    const bool ok = row_ok[i] && ih >= 0 && ih < a.H && iw >= 0 && iw < a.W;
-                    const int rl = 4 * i + sub;
-                    cp_async16(slot + rl * 128 + ((chunk ^ (rl & 7)) << 4), ok ? (const void *)(a.in + row_off[i] + tap_off) : (const void *)a.in,
-                               ok ? 16 : 0);
+                    bool ok = (ok_mask >> i) & 1u;
+                    if (padded) {
+                        const int ih = row_ih0[i] + is_rr, iw = row_iw0[i] + is_ss;
+                        ok = ok && ih >= 0 && ih < a.H && iw >= 0 && iw < a.W;
+                    }
+                    const float *src = a.in + (ok ? (uint32_t)(row_base[i] + is_off) : 0u);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(slot + row_dst[i]), "l"(src), "r"(ok ? 16 : 0) : "memory");
+                }
+                ++is_kb;
+                is_c0 += TBK; is_off += TBK;
+                if (is_c0 == a.C) {
+                    is_c0 = 0;
+                    if (++is_ss == a.KW) { is_ss = 0; ++is_rr; is_off += wrap_step - TBK; }
                 }
             }
             cp_async_commit();
         };
 #pragma unroll
-        for (int p = 0; p < DA; ++p) issue_a(p);
+        for (int p = 0; p < DA; ++p) issue_a();
         const uint32_t lane_addr = ((uint32_t)(warp * 32)) << 16;
+        uint32_t lds_off[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) lds_off[j] = (uint32_t)(lane * 128 + ((j ^ (lane & 7)) << 4));
         for (int kb = 0; kb < nkb; ++kb) {
             cp_async_wait<DA - 1>();
             __syncwarp();
@@ -492,11 +512,11 @@ conv_gemm_tc2_kernel(const ConvArgs a)
             uint32_t v[32], hi[32];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const uint4 q = *reinterpret_cast<const uint4 *>(slot + lane * 128 + ((j ^ (lane & 7)) << 4));
+                const uint4 q = *reinterpret_cast<const uint4 *>(slot + lds_off[j]);
                 v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
             }
             __syncwarp();                                    // slot fully read before it is refilled
-            issue_a(kb + DA);
+            issue_a();
 #pragma unroll
             for (int j = 0; j < 32; ++j) hi[j] = v[j] & 0xFFFFE000u;
             const int st = kb % ST;
