@@ -413,7 +413,7 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int BN, int DA, int SB, int ST>
-__global__ void __launch_bounds__(160, (BN <= 64 ? 2 : 1))
+__global__ void __launch_bounds__(160, (Tc2Cfg<BN, DA, SB, ST>::TMEM_COLS <= 256 ? 2 : 1))
 conv_gemm_tc2_kernel(const ConvArgs a)
 {
     using Cfg = Tc2Cfg<BN, DA, SB, ST>;
@@ -505,11 +505,15 @@ conv_gemm_tc2_kernel(const ConvArgs a)
         uint32_t lds_off[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) lds_off[j] = (uint32_t)(lane * 128 + ((j ^ (lane & 7)) << 4));
-        for (int kb = 0; kb < nkb; ++kb) {
+        // Software pipeline: the TMEM stores of k-block kb are issued, then the ring slot of kb+1 is
+        // read and split while they drain; only then tcgen05.wait::st + arrive.  The per-warp critical
+        // path per k-block is max(store latency, load+split) instead of their sum.
+        uint32_t hi[32], lo[32];
+        auto load_split = [&](int kb) {
             cp_async_wait<DA - 1>();
             __syncwarp();
             const unsigned char *slot = my_ring + (kb % DA) * Cfg::A_SLOT;
-            uint32_t v[32], hi[32];
+            uint32_t v[32];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const uint4 q = *reinterpret_cast<const uint4 *>(slot + lds_off[j]);
@@ -518,15 +522,20 @@ conv_gemm_tc2_kernel(const ConvArgs a)
             __syncwarp();                                    // slot fully read before it is refilled
             issue_a();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) hi[j] = v[j] & 0xFFFFE000u;
+            for (int j = 0; j < 32; ++j) {
+                hi[j] = v[j] & 0xFFFFE000u;
+                lo[j] = __float_as_uint(__uint_as_float(v[j]) - __uint_as_float(hi[j]));
+            }
+        };
+        load_split(0);
+        for (int kb = 0; kb < nkb; ++kb) {
             const int st = kb % ST;
             mbar_wait(&emptyA[st], ((kb / ST) & 1) ^ 1, 1);
             tc_fence_after();
             const uint32_t ta = tmem_base + lane_addr + Cfg::ACC_COLS + st * 2 * TBK;
             tmem_st32(ta, hi);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) hi[j] = __float_as_uint(__uint_as_float(v[j]) - __uint_as_float(hi[j]));
-            tmem_st32(ta + TBK, hi);
+            tmem_st32(ta + TBK, lo);
+            if (kb + 1 < nkb) load_split(kb + 1);            // overlaps the TMEM store latency
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             mbar_arrive(&fullA[st]);
@@ -593,6 +602,7 @@ conv_gemm_tc2_kernel(const ConvArgs a)
         // smem operand image ([n-tile][k-block][hi|lo][BN x 128 B, SWIZZLE_128B]); one stage is then a
         // single 1-D bulk copy (async proxy, completes on an mbarrier) instead of BN*16 cp.async.
         constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+        constexpr uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
         if (lane == 0) {
             const unsigned char *wt = reinterpret_cast<const unsigned char *>(a.wt_tiled) +
                                       (size_t)blockIdx.y * nkb * Cfg::B_STAGE;
@@ -613,13 +623,16 @@ conv_gemm_tc2_kernel(const ConvArgs a)
                 mbar_wait(&fullA[st], (kb / ST) & 1, 3);
                 tc_fence_after();
                 const uint32_t bs = smem_u32(b_ring + sl * Cfg::B_STAGE);
-                const uint64_t dbh = make_sw128_desc(bs), dbl = make_sw128_desc(bs + Cfg::B_TILE);
+                const uint64_t dbh = make_sw128_desc(bs);
+                // The kernel is bound by the issue rate of this one thread, so instructions are made as
+                // large as possible: the B stage is [hi rows | lo rows] and the accumulators are
+                // [D_main | D_lo] in adjacent TMEM columns, hence Ah.Bh and Ah.Bl are ONE MMA of width
+                // 2*BN (D_main += Ah.Bh, D_lo += Ah.Bl); Al.Bh follows into D_lo.
 #pragma unroll
                 for (int kk = 0; kk < TBK / 8; ++kk) {
                     const uint32_t first = (kb > 0 || kk > 0) ? 1u : 0u;
                     const uint32_t ta = tmem_base + Cfg::ACC_COLS + st * 2 * TBK + kk * 8;
-                    umma_tf32_ts(d_main, ta, dbh + 2 * kk, idesc, first);                 // Ah.Bh
-                    umma_tf32_ts(d_lo, ta, dbl + 2 * kk, idesc, first);                   // Ah.Bl
+                    umma_tf32_ts(d_main, ta, dbh + 2 * kk, idesc2, first);                // Ah.[Bh | Bl]
                     umma_tf32_ts(d_lo, ta + TBK, dbh + 2 * kk, idesc, 1u);                // Al.Bh
                 }
                 umma_commit(&emptyA[st]);
@@ -715,7 +728,7 @@ int iss_launch_conv_tc(const ConvArgs &a, int mode, cudaStream_t st)
     // BN: the widest of {256,128,64,32} dividing N
     // two accumulators per tile (main + correction) => BN <= 128 (2 x 128 + A ring <= 512 TMEM columns)
     if (ts) {
-        if (a.N % 128 == 0) return launch_tc2<128, 4, 4, 2>(a, st);      // 193 KB smem, 384 -> 512 TMEM cols, 1 CTA/SM
+        if (a.N % 128 == 0) return launch_tc2<128, 4, 4, 4>(a, st);      // 193 KB smem, 512 TMEM cols (2x128 acc + 4 A stages), 1 CTA/SM
         if (a.N % 64 == 0) return launch_tc2<64, 3, 3, 2>(a, st);        //  97 KB smem, 256 TMEM cols, 2 CTAs/SM
         return launch_tc2<32, 3, 4, 3>(a, st);                            //  81 KB smem, 256 TMEM cols
     }
