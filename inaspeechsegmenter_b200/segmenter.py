@@ -24,7 +24,6 @@ from . import _lib, engine, models
 from .export_funcs import seg2csv, seg2textgrid
 from .io import media2sig16kmono
 from .sidekit_mfcc import SidekitFrontEnd
-from .thread_returning import ThreadReturning
 
 PATCH_W = 68
 
@@ -283,55 +282,69 @@ class Segmenter:
         return t_batch_dur, nb_processed, avg, lmsg
 
 
-def medialist2feats(lin, lout, ffmpeg, skipifexist, nbtry, trydelay, device=0, fft_precision=_lib.FFT_FP64):
-    """To be used when processing batches (segmenter.py:338-374): existing
-    outputs are skipped, failing inputs are retried nbtry times and reported
-    with code 2 instead of raising."""
-    ret = None
-    msg = []
-    while ret is None and len(lin) > 0:
-        src = lin.pop(0)
-        dst = lout.pop(0)
+class _FeaturePrefetcher:
+    """Depth-1 prefetch of the per-file front-end (decode -> pinned upload -> K1 on a side
+    context) while the main thread segments the previous file: the role of the reference's
+    ``medialist2feats`` / ``featGenerator`` pair (segmenter.py:338-387), with the same message
+    protocol -- one ``(dst, code, text)`` per consumed input, code 0 = features ready,
+    1 = output already exists (skipped), 2 = every attempt failed."""
 
-        if skipifexist and os.path.exists(dst):
-            msg.append((dst, 1, 'already exists'))
-            continue
+    def __init__(self, sources, destinations, ffmpeg, skipifexist, nbtry, trydelay, device, fft_precision):
+        from concurrent.futures import ThreadPoolExecutor
+        self._todo = list(zip(sources, destinations))
+        self._opt = (ffmpeg, skipifexist, max(1, nbtry), trydelay, device, fft_precision)
+        self._pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix='iss-feat')
+        self._next = self._pool.submit(self._advance)
 
-        dname = os.path.dirname(dst)
-        if not os.path.isdir(dname):
-            os.makedirs(dname)
-
-        itry = 0
-        while ret is None and itry < nbtry:
+    def _extract(self, src):
+        ffmpeg, _, nbtry, trydelay, device, fft_precision = self._opt
+        last = None
+        for attempt in range(nbtry):
             try:
-                ret = _media2feats(src, None, None, ffmpeg, device, fft_precision, 'feat')
-                torch.cuda.current_stream(ret[0].device).synchronize()     # hand-off to the main thread
-            except:                                                       # noqa: E722 (reference behaviour, :364)
-                itry += 1
-                errmsg = sys.exc_info()[0]
-                if itry != nbtry:
+                feats = _media2feats(src, None, None, ffmpeg, device, fft_precision, 'feat')
+                torch.cuda.current_stream(feats[0].device).synchronize()      # hand-off to the main thread
+                return feats, None
+            except BaseException:                                              # same catch-all as the reference (:364)
+                last = sys.exc_info()[0]
+                if attempt + 1 < nbtry:
                     time.sleep(random.random() * trydelay)
-        if ret is None:
-            msg.append((dst, 2, 'error: ' + str(errmsg)))
-        else:
-            msg.append((dst, 0, 'ok'))
+        return None, last
 
-    return ret, msg
+    def _advance(self):
+        """Consume inputs until one yields features (or none are left)."""
+        skipifexist = self._opt[1]
+        log = []
+        while self._todo:
+            src, dst = self._todo.pop(0)
+            if skipifexist and os.path.exists(dst):
+                log.append((dst, 1, 'already exists'))
+                continue
+            parent = os.path.dirname(dst)
+            if not os.path.isdir(parent):
+                os.makedirs(parent)
+            feats, err = self._extract(src)
+            if feats is None:
+                log.append((dst, 2, 'error: ' + str(err)))
+                continue
+            log.append((dst, 0, 'ok'))
+            return feats, log
+        return None, log
+
+    def __iter__(self):
+        try:
+            while True:
+                feats, log = self._next.result()
+                more = bool(self._todo)
+                if more:
+                    self._next = self._pool.submit(self._advance)
+                yield feats, log
+                if not more:
+                    return
+        finally:
+            self._pool.shutdown(wait=False)
 
 
 def featGenerator(ilist, olist, ffmpeg='ffmpeg', skipifexist=False, nbtry=1, trydelay=2., device=0,
                   fft_precision=_lib.FFT_FP64):
-    """Depth-1 prefetch: the next file is decoded, uploaded and run through K1
-    on a worker thread while the main thread segments the current one
-    (segmenter.py:377-387)."""
-    args = [ilist, olist, ffmpeg, skipifexist, nbtry, trydelay, device, fft_precision]
-    thread = ThreadReturning(target=medialist2feats, args=args)
-    thread.start()
-    while True:
-        ret, msg = thread.join()
-        if len(ilist) == 0:
-            break
-        thread = ThreadReturning(target=medialist2feats, args=args)
-        thread.start()
-        yield ret, msg
-    yield ret, msg
+    """Name kept for users of the reference helper (segmenter.py:377-387)."""
+    return iter(_FeaturePrefetcher(ilist, olist, ffmpeg, skipifexist, nbtry, trydelay, device, fft_precision))
