@@ -54,6 +54,9 @@ SIGNATURES = {
     'iss_energy_viterbi': (_i, [_vp, _vp, _i64, _vp, _d, _vp, _vp, _d, _i, _vp, _vp, _vp]),
     'iss_viterbi_segments': (_i, [_vp, _vp, _i, _vp, _i, _vp, _d, _vp, _vp, _vp]),
     'iss_viterbi_work_bytes': (_i64, [_i64, _i]),
+    'iss_energy_transfer': (_i, [_vp, _vp, _i64, _vp, _d, _vp, _vp, _vp, _vp, _vp]),
+    'iss_energy_forward': (_i, [_vp, _vp, _i64, _vp, _d, _vp, _vp, _d, _vp, _vp, _vp, _vp, _vp]),
+    'iss_energy_emit': (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp]),
     'iss_cnn_create': (_i, [_vp, _c.POINTER(LayerDesc), _i, _vp, _i64, _i, _i, _c.POINTER(_vp)]),
     'iss_cnn_destroy': (_i, [_vp]),
     'iss_cnn_num_classes': (_i, [_vp]),

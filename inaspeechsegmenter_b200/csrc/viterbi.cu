@@ -38,6 +38,11 @@ struct VitLayout {
     int64_t *seg_off;              // [n_seg+1]
     int64_t *chunk_off;            // [n_seg+1]
     uint8_t *last;                 // [n_seg] argmax V[T-1]
+    // partial-chain support (time-sharded recordings)
+    const double *vin;             // [n_seg][MAXK] incoming scores (continue from a predecessor) or nullptr
+    double *vout;                  // [n_seg][MAXK] outgoing scores V[T-1] or nullptr
+    int alias;                     // 1: every block walks the SAME range seg_off[0..1] (basis chains of a transfer matrix)
+    int store_bp;                  // 0: scores only
 };
 
 __device__ __forceinline__ bool better(double c, double best)
@@ -51,9 +56,10 @@ __global__ void __launch_bounds__(32)
 viterbi_forward_kernel(const float *__restrict__ src, const double *__restrict__ stats, VitParams prm, VitLayout lay)
 {
     const int seg = blockIdx.x, lane = threadIdx.x;
-    const int64_t t0 = lay.seg_off[seg];
-    const int64_t T = lay.seg_off[seg + 1] - t0;
+    const int64_t t0 = lay.alias ? lay.seg_off[0] : lay.seg_off[seg];
+    const int64_t T = (lay.alias ? lay.seg_off[1] : lay.seg_off[seg + 1]) - t0;
     if (T <= 0) return;
+    const bool cont = lay.vin != nullptr;          // first step is an ordinary transition from vin
     double thr = 0.0;
     if (ENERGY) {
         // np.mean(f32 array) is f32; + np.log(ratio) (f64) promotes to f64 (segmenter.py:70)
@@ -63,7 +69,7 @@ viterbi_forward_kernel(const float *__restrict__ src, const double *__restrict__
     }
     double V[K];
 #pragma unroll
-    for (int j = 0; j < K; ++j) V[j] = 0.0;
+    for (int j = 0; j < K; ++j) V[j] = cont ? lay.vin[seg * MAXK + j] : 0.0;
 
     for (int64_t base = 0; base < T; base += 32) {
         const int64_t t = base + lane;
@@ -113,7 +119,7 @@ viterbi_forward_kernel(const float *__restrict__ src, const double *__restrict__
             }
             return bp;
         };
-        if (nstep == 32 && base > 0) {
+        if (nstep == 32 && (base > 0 || cont)) {
             // full block, fully unrolled: the 32 x K emission shuffles do not depend on V, so they are
             // issued ahead and only the add/compare/select chain remains on the serial critical path
 #pragma unroll
@@ -129,11 +135,11 @@ viterbi_forward_kernel(const float *__restrict__ src, const double *__restrict__
                 double es[K];
 #pragma unroll
                 for (int j = 0; j < K; ++j) es[j] = __shfl_sync(0xffffffffu, e[j], s);
-                const unsigned bp = dp_step(es, base + s == 0);
+                const unsigned bp = dp_step(es, base + s == 0 && !cont);
                 if (lane == s) mybp = bp;
             }
         }
-        if (t < T) lay.bp[t0 + t] = (uint8_t)mybp;
+        if (t < T && lay.store_bp) lay.bp[t0 + t] = (uint8_t)mybp;
     }
     if (lane == 0) {
         int arg = 0;
@@ -144,7 +150,11 @@ viterbi_forward_kernel(const float *__restrict__ src, const double *__restrict__
             best = u ? V[k] : best;
             arg = u ? k : arg;
         }
-        lay.last[seg] = (uint8_t)arg;
+        if (lay.store_bp) lay.last[seg] = (uint8_t)arg;
+        if (lay.vout) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) lay.vout[seg * MAXK + k] = V[k];
+        }
     }
 }
 
@@ -159,7 +169,7 @@ __device__ __forceinline__ int find_seg(const int64_t *chunk_off, int n_seg, int
 }
 
 // cmap[c]: (state at the last step of chunk c) -> (state at the last step of chunk c-1)
-__global__ void viterbi_chunk_map_kernel(VitLayout lay, int n_seg, int64_t nchunks)
+__global__ void viterbi_chunk_map_kernel(VitLayout lay, int n_seg, int64_t nchunks, int has_pred)
 {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nchunks) return;
@@ -170,7 +180,7 @@ __global__ void viterbi_chunk_map_kernel(VitLayout lay, int n_seg, int64_t nchun
     unsigned m = 0xE4;                                      // identity: 3,2,1,0 in 2-bit fields
     const uint8_t *bp = lay.bp + t0;
     for (int64_t t = b - 1; t >= a; --t) {
-        if (t == 0) break;                                  // bp[0] is unused (no predecessor)
+        if (t == 0 && !has_pred) break;                     // bp[0] is unused when the sequence has no predecessor
         const unsigned f = bp[t];
         unsigned r = 0;
 #pragma unroll
@@ -251,7 +261,7 @@ int run_backtrack(const VitLayout &lay, const HostPlan &hp, int n_seg, int out_s
     if (hp.nchunks == 0) return ISS_OK;
     const int TB = 128;
     const unsigned gc = (unsigned)((hp.nchunks + TB - 1) / TB);
-    viterbi_chunk_map_kernel<<<gc, TB, 0, st>>>(lay, n_seg, hp.nchunks);
+    viterbi_chunk_map_kernel<<<gc, TB, 0, st>>>(lay, n_seg, hp.nchunks, 0);
     viterbi_chunk_scan_kernel<<<(n_seg + 63) / 64, 64, 0, st>>>(lay, n_seg);
     viterbi_chunk_emit_kernel<<<gc, TB, 0, st>>>(lay, n_seg, hp.nchunks, out_stride, d_states);
     ISS_CUDA_OK(cudaGetLastError());
@@ -259,13 +269,130 @@ int run_backtrack(const VitLayout &lay, const HostPlan &hp, int n_seg, int out_s
     return ISS_OK;
 }
 
+// composite of all chunk maps of sequence 0: (state at the last step) -> (state just before the first step)
+__global__ void viterbi_compose_kernel(VitLayout lay, int64_t nchunks, uint8_t *out)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    unsigned m = 0xE4;
+    for (int64_t c = nchunks - 1; c >= 0; --c) {
+        const unsigned f = lay.cmap[c];
+        unsigned r = 0;
+#pragma unroll
+        for (int x = 0; x < 4; ++x) r |= ((f >> (2 * ((m >> (2 * x)) & 3))) & 3) << (2 * x);
+        m = r;
+    }
+    out[0] = (uint8_t)m;
+}
+
+__global__ void viterbi_set_last_kernel(VitLayout lay, int state) { if (threadIdx.x == 0 && blockIdx.x == 0) lay.last[0] = (uint8_t)state; }
+
 }  // namespace
+
+// ---- partial chains of the energy Viterbi for time-sharded recordings -------------------
+static void fill_energy_params(VitParams &prm, const double *h_emis, const double *h_trans, double log_prior, double log_ratio)
+{
+    for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) prm.A[i][j] = h_trans[i * 2 + j];
+    prm.prior = log_prior; prm.emis_hit = h_emis[0]; prm.emis_miss = h_emis[1]; prm.log_ratio = log_ratio;
+}
+
+extern "C" int iss_energy_transfer(iss_ctx *ctx, const float *d_loge, int64_t L, const double *d_loge_stats,
+                                   double log_ratio, const double *h_emis, const double *h_trans,
+                                   double *h_matrix, void *d_work, void *stream)
+{
+    ISS_REQUIRE(ctx && d_loge && d_loge_stats && h_emis && h_trans && h_matrix && d_work && L > 0, ISS_ERR_INVALID, "iss_energy_transfer: bad argument");
+    ISS_CUDA_OK(cudaSetDevice(ctx->device));
+    cudaStream_t st = iss_stream(stream);
+    const int64_t off[2] = {0, L};
+    HostPlan hp; VitLayout lay = {};
+    int rc = make_layout(off, 1, d_work, hp, lay, st);
+    if (rc != ISS_OK) return rc;
+    // scratch for vin / vout lives behind `last`
+    double *d_v = reinterpret_cast<double *>(lay.last + 256);
+    const double NEG_INF = -INFINITY;
+    double vin[2 * MAXK] = {0.0, NEG_INF, 0, 0, NEG_INF, 0.0, 0, 0};      // basis vectors e_0, e_1 (max-plus)
+    ISS_CUDA_OK(cudaMemcpyAsync(d_v, vin, sizeof(vin), cudaMemcpyHostToDevice, st));
+    lay.vin = d_v; lay.vout = d_v + 2 * MAXK; lay.alias = 1; lay.store_bp = 0;
+    VitParams prm = {};
+    fill_energy_params(prm, h_emis, h_trans, 0.0, log_ratio);
+    viterbi_forward_kernel<2, true><<<2, 32, 0, st>>>(d_loge, d_loge_stats, prm, lay);
+    ISS_CUDA_OK(cudaGetLastError());
+    iss_count_launch();
+    double vout[2 * MAXK];
+    ISS_CUDA_OK(cudaMemcpyAsync(vout, lay.vout, sizeof(vout), cudaMemcpyDeviceToHost, st));
+    ISS_CUDA_OK(cudaStreamSynchronize(st));
+    // M[j][i] = score of ending in j having started (before the first frame) in i
+    for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) h_matrix[j * 2 + i] = vout[i * MAXK + j];
+    return ISS_OK;
+}
+
+extern "C" int iss_energy_forward(iss_ctx *ctx, const float *d_loge, int64_t L, const double *d_loge_stats,
+                                  double log_ratio, const double *h_emis, const double *h_trans, double log_prior,
+                                  const double *h_vin, double *h_vout, uint8_t *h_backmap, void *d_work, void *stream)
+{
+    ISS_REQUIRE(ctx && d_loge && d_loge_stats && h_emis && h_trans && h_vout && h_backmap && d_work && L > 0, ISS_ERR_INVALID, "iss_energy_forward: bad argument");
+    ISS_CUDA_OK(cudaSetDevice(ctx->device));
+    cudaStream_t st = iss_stream(stream);
+    const int64_t off[2] = {0, L};
+    HostPlan hp; VitLayout lay = {};
+    int rc = make_layout(off, 1, d_work, hp, lay, st);
+    if (rc != ISS_OK) return rc;
+    double *d_v = reinterpret_cast<double *>(lay.last + 256);
+    if (h_vin) {
+        double vin[MAXK] = {h_vin[0], h_vin[1], 0, 0};
+        ISS_CUDA_OK(cudaMemcpyAsync(d_v, vin, sizeof(vin), cudaMemcpyHostToDevice, st));
+        lay.vin = d_v;
+    }
+    lay.vout = d_v + 2 * MAXK; lay.alias = 0; lay.store_bp = 1;
+    VitParams prm = {};
+    fill_energy_params(prm, h_emis, h_trans, log_prior, log_ratio);
+    viterbi_forward_kernel<2, true><<<1, 32, 0, st>>>(d_loge, d_loge_stats, prm, lay);
+    const unsigned gc = (unsigned)((hp.nchunks + 127) / 128);
+    viterbi_chunk_map_kernel<<<gc, 128, 0, st>>>(lay, 1, hp.nchunks, h_vin ? 1 : 0);
+    uint8_t *d_map = reinterpret_cast<uint8_t *>(d_v + 4 * MAXK);
+    viterbi_compose_kernel<<<1, 32, 0, st>>>(lay, hp.nchunks, d_map);
+    ISS_CUDA_OK(cudaGetLastError());
+    iss_count_launch(3);
+    double vout[MAXK];
+    uint8_t m;
+    ISS_CUDA_OK(cudaMemcpyAsync(vout, lay.vout, sizeof(vout), cudaMemcpyDeviceToHost, st));
+    ISS_CUDA_OK(cudaMemcpyAsync(&m, d_map, 1, cudaMemcpyDeviceToHost, st));
+    ISS_CUDA_OK(cudaStreamSynchronize(st));
+    h_vout[0] = vout[0]; h_vout[1] = vout[1];
+    h_backmap[0] = m & 3; h_backmap[1] = (m >> 2) & 3;
+    return ISS_OK;
+}
+
+extern "C" int iss_energy_emit(iss_ctx *ctx, int64_t L, int end_state, int out_stride, uint8_t *d_states,
+                               void *d_work, void *stream)
+{
+    ISS_REQUIRE(ctx && d_states && d_work && L > 0 && out_stride >= 1 && end_state >= -1 && end_state < 2, ISS_ERR_INVALID, "iss_energy_emit: bad argument");
+    ISS_CUDA_OK(cudaSetDevice(ctx->device));
+    cudaStream_t st = iss_stream(stream);
+    // same carve as iss_energy_forward (no copies: the tables are already on the device)
+    HostPlan hp; VitLayout lay = {};
+    hp.seg_off = {0, L}; hp.chunk_off = {0, (L + CH - 1) / CH}; hp.total = L; hp.nchunks = (L + CH - 1) / CH;
+    uint8_t *p = reinterpret_cast<uint8_t *>(d_work);
+    size_t o = 0;
+    lay.bp = p + o;        o = align_up(o + (size_t)hp.total, 256);
+    lay.cmap = p + o;      o = align_up(o + (size_t)hp.nchunks, 256);
+    lay.cend = p + o;      o = align_up(o + (size_t)hp.nchunks, 256);
+    lay.seg_off = reinterpret_cast<int64_t *>(p + o);   o = align_up(o + sizeof(int64_t) * 2, 256);
+    lay.chunk_off = reinterpret_cast<int64_t *>(p + o); o = align_up(o + sizeof(int64_t) * 2, 256);
+    lay.last = p + o;
+    if (end_state >= 0) viterbi_set_last_kernel<<<1, 32, 0, st>>>(lay, end_state);
+    const unsigned gc = (unsigned)((hp.nchunks + 127) / 128);
+    viterbi_chunk_scan_kernel<<<1, 64, 0, st>>>(lay, 1);
+    viterbi_chunk_emit_kernel<<<gc, 128, 0, st>>>(lay, 1, hp.nchunks, out_stride, d_states);
+    ISS_CUDA_OK(cudaGetLastError());
+    iss_count_launch(3);
+    return ISS_OK;
+}
 
 extern "C" int64_t iss_viterbi_work_bytes(int64_t total_steps, int n_seg)
 {
     if (total_steps < 0 || n_seg < 0) return -1;
     const int64_t nc = total_steps / CH + n_seg + 1;
-    return total_steps + 2 * nc + 2 * (int64_t)sizeof(int64_t) * (n_seg + 1) + n_seg + 8 * 256;
+    return total_steps + 2 * nc + 2 * (int64_t)sizeof(int64_t) * (n_seg + 1) + n_seg + 8 * 256 + 1024 /* vin/vout/map scratch */;
 }
 
 extern "C" int iss_energy_viterbi(iss_ctx *ctx, const float *d_loge, int64_t L, const double *d_loge_stats,
@@ -280,9 +407,10 @@ extern "C" int iss_energy_viterbi(iss_ctx *ctx, const float *d_loge, int64_t L, 
     ISS_CUDA_OK(cudaSetDevice(ctx->device));
     cudaStream_t st = iss_stream(stream);
     const int64_t off[2] = {0, L};
-    HostPlan hp; VitLayout lay;
+    HostPlan hp; VitLayout lay = {};
     int rc = make_layout(off, 1, d_work, hp, lay, st);
     if (rc != ISS_OK) return rc;
+    lay.store_bp = 1;
     VitParams prm = {};
     for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) prm.A[i][j] = h_trans[i * 2 + j];
     prm.prior = log_prior; prm.emis_hit = h_emis[0]; prm.emis_miss = h_emis[1]; prm.log_ratio = log_ratio;
@@ -302,9 +430,10 @@ extern "C" int iss_viterbi_segments(iss_ctx *ctx, const float *d_probs, int K, c
     ISS_REQUIRE(d_probs && d_states && d_work, ISS_ERR_INVALID, "iss_viterbi_segments: NULL buffer");
     ISS_CUDA_OK(cudaSetDevice(ctx->device));
     cudaStream_t st = iss_stream(stream);
-    HostPlan hp; VitLayout lay;
+    HostPlan hp; VitLayout lay = {};
     int rc = make_layout(h_seg_off, n_seg, d_work, hp, lay, st);
     if (rc != ISS_OK) return rc;
+    lay.store_bp = 1;
     VitParams prm = {};
     for (int i = 0; i < K; ++i) for (int j = 0; j < K; ++j) prm.A[i][j] = h_trans[i * K + j];
     prm.prior = log_prior;

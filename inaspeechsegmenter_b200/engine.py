@@ -169,3 +169,47 @@ def viterbi_segments(ctx, probs, seg_off, trans, stream=None):
                                         _lib.ptr(trans), prior, _lib.ptr(states), _lib.ptr(work),
                                         _stream_ptr(probs.device, stream)), 'iss_viterbi_segments')
     return states
+
+
+# ---- partial energy chains for time-sharded recordings (shard.py) ---------------------------------
+def _energy_consts(energy_ratio):
+    trans = np.ascontiguousarray(log_trans_exp(150, cost0=-5), dtype=np.float64)
+    return trans, float(np.log(np.ones(2) / 2)[0]), float(np.log(energy_ratio))
+
+
+def energy_transfer(ctx, loge, stats, energy_ratio, stream=None):
+    """2x2 max-plus transfer matrix (numpy float64, M[j, i]) of this slice of the energy chain."""
+    lib = _lib.load()
+    L = loge.numel()
+    trans, _, lr = _energy_consts(energy_ratio)
+    work = ctx.workspace('vit_energy', lib.iss_viterbi_work_bytes(L, 1))
+    M = np.zeros(4, dtype=np.float64)
+    _lib.check(lib.iss_energy_transfer(ctx.handle, _lib.ptr(loge), L, _lib.ptr(stats), lr, _lib.ptr(_EMIS), _lib.ptr(trans),
+                                       _lib.ptr(M), _lib.ptr(work), _stream_ptr(loge.device, stream)), 'iss_energy_transfer')
+    return M.reshape(2, 2)
+
+
+def energy_forward(ctx, loge, stats, energy_ratio, vin=None, stream=None):
+    """True forward pass over this slice; returns (vout[2] float64, backmap[2] uint8)."""
+    lib = _lib.load()
+    L = loge.numel()
+    trans, prior, lr = _energy_consts(energy_ratio)
+    work = ctx.workspace('vit_energy', lib.iss_viterbi_work_bytes(L, 1))
+    vout = np.zeros(2, dtype=np.float64)
+    bmap = np.zeros(2, dtype=np.uint8)
+    vin_arr = None if vin is None else np.ascontiguousarray(vin, dtype=np.float64)
+    _lib.check(lib.iss_energy_forward(ctx.handle, _lib.ptr(loge), L, _lib.ptr(stats), lr, _lib.ptr(_EMIS), _lib.ptr(trans), prior,
+                                      _lib.ptr(vin_arr), _lib.ptr(vout), _lib.ptr(bmap), _lib.ptr(work),
+                                      _stream_ptr(loge.device, stream)), 'iss_energy_forward')
+    return vout, bmap
+
+
+def energy_emit(ctx, loge, end_state, out_stride=2, stream=None):
+    """Backtrack the slice decoded by the preceding energy_forward (same context) -> CUDA uint8 track."""
+    lib = _lib.load()
+    L = loge.numel()
+    states = torch.empty(((L + out_stride - 1) // out_stride,), dtype=torch.uint8, device=loge.device)
+    work = ctx.workspace('vit_energy', lib.iss_viterbi_work_bytes(L, 1))
+    _lib.check(lib.iss_energy_emit(ctx.handle, L, int(end_state), int(out_stride), _lib.ptr(states), _lib.ptr(work),
+                                   _stream_ptr(loge.device, stream)), 'iss_energy_emit')
+    return states

@@ -118,6 +118,20 @@ class Comm:
         return torch.cat([b[:c] for b, c in zip(bufs, counts)])
 
 
+    def all_gather_fixed(self, arr):
+        """All-gather of a small fixed-size float64 numpy vector -> [world, n] numpy array."""
+        if self.world == 1:
+            return np.asarray(arr, dtype=np.float64)[None]
+        dev = self.device
+        if dist.get_backend(self.group) == 'gloo':
+            dev = 'cpu'
+        t = torch.tensor(np.asarray(arr, dtype=np.float64), device=dev)
+        bufs = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(bufs, t, group=self.group)
+        self.bytes += t.numel() * 8 * self.world
+        return np.stack([b.cpu().numpy() for b in bufs])
+
+
 class CudaBackend:
     """The product backend: libiss_b200 kernels on this rank's GPU."""
 
@@ -140,6 +154,19 @@ class CudaBackend:
     def energy_track(self, loge_global, ratio):
         stats = self.engine.loge_stats(self.ctx, loge_global)
         return self.engine.energy_viterbi(self.ctx, loge_global, stats, ratio, out_stride=2).cpu().numpy()
+
+    # -- partial energy chains (scalable variant) --
+    def loge_stats(self, loge_global):
+        return self.engine.loge_stats(self.ctx, loge_global)
+
+    def energy_transfer(self, loge_own, stats, ratio):
+        return self.engine.energy_transfer(self.ctx, loge_own, stats, ratio)
+
+    def energy_forward(self, loge_own, stats, ratio, vin):
+        return self.engine.energy_forward(self.ctx, loge_own, stats, ratio, vin)
+
+    def energy_emit(self, loge_own, end_state):
+        return self.engine.energy_emit(self.ctx, loge_own, end_state, out_stride=2)
 
     def cnn_probs(self, which, mspec_local, ranges, edge_left, edge_right):
         net = self.seg.vad.nn if which == 'vad' else self.seg.gender.nn
@@ -168,7 +195,22 @@ def _dnn_stage(backend, comm, plan, rank, which, spec, mspec_local, lseg):
         return list(lseg)
     seg_off = np.concatenate(([0], np.cumsum([b - a for a, b in sel]))).astype(np.int64)
     assert probs.shape[0] == seg_off[-1], (probs.shape, seg_off[-1])
-    states = backend.viterbi(probs, seg_off, diag_trans_exp(spec.viterbi_arg, len(spec.outlabels)))
+    trans = diag_trans_exp(spec.viterbi_arg, len(spec.outlabels))
+    if comm.world == 1 or not getattr(plan, 'shard_decode', True):
+        states = backend.viterbi(probs, seg_off, trans)
+    else:
+        # segments are independent chains: a rank decodes those that START in its patch range (the
+        # posteriors of straddling segments are already here) and the label tracks are all-gathered
+        pa, pb = plan.patch_range(rank)
+        mine = [k for k, (a, b) in enumerate(sel) if pa <= a < pb]
+        if mine:
+            k0, k1 = mine[0], mine[-1] + 1                       # contiguous because segments are time-ordered
+            local = backend.viterbi(probs[seg_off[k0]:seg_off[k1]], seg_off[k0:k1 + 1] - seg_off[k0], trans)
+        else:
+            local = np.zeros(0, dtype=np.uint8)
+        dev = probs.device if isinstance(probs, torch.Tensor) else 'cpu'
+        states = comm.all_gather_var(torch.from_numpy(np.ascontiguousarray(local, dtype=np.uint8)).to(dev)).cpu().numpy()
+        assert len(states) == seg_off[-1]
     out, k = [], 0
     for lab, a, b in lseg:
         if lab != spec.inlabel:
@@ -180,6 +222,46 @@ def _dnn_stage(backend, comm, plan, rank, which, spec, mspec_local, lseg):
     return out
 
 
+def _maxplus(M, v):
+    """(M (x) v)[j] = max_i (M[j, i] + v[i]) in float64."""
+    return np.array([max(M[j, 0] + v[0], M[j, 1] + v[1]) for j in range(2)], dtype=np.float64)
+
+
+def _energy_track_transfer(backend, comm, rank, loge_own, loge_global, ratio):
+    """Whole-file energy Viterbi (pyannote_viterbi.py:202-220) cut at rank boundaries, SURVEY 8(e):
+    rank 0 decodes its frames from the sequence start while every other rank computes the max-plus
+    transfer matrix of its frames (two basis chains); one tiny all-gather; entry scores are composed
+    on the host; every rank then runs its true forward pass; a second tiny all-gather of composite
+    back-pointer maps + the final argmax gives each rank its end state; tracks are all-gathered.
+    Exact in exact arithmetic; floating-point association differs from the single chain only in how
+    the entry scores are rounded (decisions can differ only on ~1e-16-relative near-ties)."""
+    world = comm.world
+    stats = backend.loge_stats(loge_global)                  # same kernel & order as on one GPU: identical threshold
+    if rank == 0:
+        vout, bmap = backend.energy_forward(loge_own, stats, ratio, None)
+        msg = np.concatenate((np.zeros(4), vout))
+    else:
+        msg = np.concatenate((backend.energy_transfer(loge_own, stats, ratio).ravel(), np.zeros(2)))
+    allm = comm.all_gather_fixed(msg)                         # [world, 6]
+    v = allm[0, 4:6]                                          # scores leaving rank 0
+    vins = [None, v]
+    for r in range(1, world - 1):
+        v = _maxplus(allm[r, :4].reshape(2, 2), v)
+        vins.append(v)
+    if rank > 0:
+        vout, bmap = backend.energy_forward(loge_own, stats, ratio, vins[rank])
+    tail = np.array([float(bmap[0]), float(bmap[1]), float(np.argmax(vout))])      # first max on ties, like numpy
+    allt = comm.all_gather_fixed(tail)                        # [world, 3]
+    end = [0] * world
+    end[world - 1] = int(allt[world - 1, 2])
+    for r in range(world - 2, -1, -1):
+        end[r] = int(allt[r + 1, end[r + 1]])
+    local = backend.energy_emit(loge_own, end[rank])
+    if not isinstance(local, torch.Tensor):
+        local = torch.from_numpy(np.ascontiguousarray(local, dtype=np.uint8))
+    return comm.all_gather_var(local).cpu().numpy()
+
+
 def segment_sharded(backend, comm, plan, pcm_local, vad_spec, gender_spec=None, energy_ratio=0.03, start_sec=0):
     """Segment the recording described by `plan`; `pcm_local` is this rank's
     sample_range().  Returns the full segment list (identical on every rank)."""
@@ -188,9 +270,17 @@ def segment_sharded(backend, comm, plan, pcm_local, vad_spec, gender_spec=None, 
     mspec, loge = backend.features(pcm_local)
     assert len(loge) == fb - fa, (len(loge), fa, fb)
     oa, ob = plan.owned_frames(rank)
-    loge_global = comm.all_gather_var(loge[oa - fa:ob - fa].contiguous())
+    loge_own = loge[oa - fa:ob - fa].contiguous()
+    loge_global = comm.all_gather_var(loge_own)
     assert loge_global.shape[0] == plan.L
-    track = backend.energy_track(loge_global, energy_ratio)
+    mode = getattr(plan, 'energy_mode', 'auto')
+    if mode == 'auto':
+        mode = 'transfer' if comm.world >= 3 else 'replicated'
+    if comm.world == 1 or mode == 'replicated':
+        track = backend.energy_track(loge_global, energy_ratio)
+    else:
+        track = _energy_track_transfer(backend, comm, rank, loge_own, loge_global, energy_ratio)
+        assert len(track) == plan.P, (len(track), plan.P)
     lseg = [('noEnergy' if lab == 0 else 'energy', a, b) for lab, a, b in _rle(track)]
     lseg = _dnn_stage(backend, comm, plan, rank, 'vad', vad_spec, mspec, lseg)
     if gender_spec is not None:
@@ -198,10 +288,12 @@ def segment_sharded(backend, comm, plan, pcm_local, vad_spec, gender_spec=None, 
     return [(lab, start_sec + a * .02, start_sec + b * .02) for lab, a, b in lseg]
 
 
-def segment_signal_sharded(segmenter, pcm_local, n_samples_total, group=None):
-    """Convenience wrapper for the product: `segmenter` is this rank's Segmenter."""
+def segment_signal_sharded(segmenter, pcm_local, n_samples_total, group=None, energy_mode='auto'):
+    """Convenience wrapper for the product: `segmenter` is this rank's Segmenter.
+    energy_mode: 'replicated' | 'transfer' | 'auto' (transfer matrices from 3 ranks up)."""
     comm = Comm(segmenter.ctx.device, group)
     plan = ShardPlan(n_samples_total, comm.world)
+    plan.energy_mode = energy_mode
     backend = CudaBackend(segmenter)
     gender = segmenter.gender if segmenter.detect_gender else None
     return segment_sharded(backend, comm, plan, pcm_local, segmenter.vad, gender, segmenter.energy_ratio), comm

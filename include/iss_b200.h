@@ -129,6 +129,28 @@ int iss_viterbi_segments(iss_ctx *ctx, const float *d_probs, int K, const int64_
                          void *d_work, void *stream);
 int64_t iss_viterbi_work_bytes(int64_t total_steps, int n_seg);
 
+/* Partial chains of the energy Viterbi for a recording that is time-sharded across GPUs
+ * (the whole-file chain of pyannote_viterbi.py:202-220 cut at rank boundaries):
+ *  iss_energy_transfer: max-plus transfer matrix of this rank's L frames, h_matrix[j*2+i] = best
+ *      score of ending in state j given the chain entered (before the first frame) in state i --
+ *      two basis-vector forward chains, no back-pointers.  Synchronous.
+ *  iss_energy_forward: the true forward pass over the L frames, from the sequence start
+ *      (h_vin == NULL: V[0] = E[0] + log_prior) or continuing from the predecessor's outgoing
+ *      scores h_vin[2]; stores back-pointers in d_work, returns the outgoing scores h_vout[2] and
+ *      the composite back map h_backmap[x] = state just before the first frame given state x at
+ *      the last frame.  Synchronous.
+ *  iss_energy_emit: backtrack from end_state (-1: argmax of the outgoing scores of the preceding
+ *      iss_energy_forward on the same d_work) and write every out_stride-th state.
+ * d_work: iss_viterbi_work_bytes(L, 1) bytes, the same buffer for forward and emit. */
+int iss_energy_transfer(iss_ctx *ctx, const float *d_loge, int64_t L, const double *d_loge_stats,
+                        double log_ratio, const double *h_emis, const double *h_trans,
+                        double *h_matrix, void *d_work, void *stream);
+int iss_energy_forward(iss_ctx *ctx, const float *d_loge, int64_t L, const double *d_loge_stats,
+                       double log_ratio, const double *h_emis, const double *h_trans, double log_prior,
+                       const double *h_vin, double *h_vout, uint8_t *h_backmap, void *d_work, void *stream);
+int iss_energy_emit(iss_ctx *ctx, int64_t L, int end_state, int out_stride, uint8_t *d_states,
+                    void *d_work, void *stream);
+
 /* ---- K2: patch z-normalisation + CNN forward ------------------------------
  * Replaces _get_patches (segmenter.py:76-88) + keras Model.predict
  * (segmenter.py:131-133,163) + the non-finite override (:175). */

@@ -42,6 +42,58 @@ class OracleBackend:
         from oracle import segmenter_oracle as so
         return so.energy_activity(loge_global.numpy(), ratio)[::2].astype(np.uint8)
 
+    # ---- partial energy chains (numpy restatement of the same DP, for the 'transfer' mode) ----
+    def loge_stats(self, loge_global):
+        return loge_global.numpy()
+
+    def _emissions(self, loge_own, loge_global_np, ratio):
+        from oracle import viterbi_oracle as vo
+        g = loge_global_np
+        thr = np.mean(g[np.isfinite(g)]) + np.log(ratio)                # segmenter.py:70
+        return vo.pred2logemission(loge_own.numpy() > thr), vo.log_trans_exp(150, cost0=-5)
+
+    def _run(self, em, A, V, first_is_init):
+        bps = np.zeros((len(em), 2), dtype=np.int64)
+        for t in range(len(em)):
+            if t == 0 and first_is_init:
+                V = em[0] + np.log(np.ones(2) / 2)
+                bps[0] = (0, 1)
+            else:
+                cand = V[:, None] + A
+                bps[t] = np.argmax(cand, axis=0)
+                V = em[t] + cand[bps[t], np.arange(2)]
+        return V, bps
+
+    def energy_transfer(self, loge_own, stats, ratio):
+        em, A = self._emissions(loge_own, stats, ratio)
+        M = np.zeros((2, 2))
+        for i in range(2):
+            v0 = np.full(2, -np.inf)
+            v0[i] = 0.0
+            M[:, i] = self._run(em, A, v0, False)[0]
+        return M
+
+    def energy_forward(self, loge_own, stats, ratio, vin):
+        em, A = self._emissions(loge_own, stats, ratio)
+        V, bps = self._run(em, A, None if vin is None else np.asarray(vin, dtype=np.float64), vin is None)
+        self._bps, self._vout = bps, V
+        bmap = np.zeros(2, dtype=np.uint8)
+        for x in range(2):
+            s_ = x
+            for t in range(len(em) - 1, 0 if vin is None else -1, -1):
+                s_ = bps[t, s_]
+            bmap[x] = s_
+        return V, bmap
+
+    def energy_emit(self, loge_own, end_state):
+        x = int(np.argmax(self._vout)) if end_state < 0 else int(end_state)
+        T = len(self._bps)
+        st = np.zeros(T, dtype=np.uint8)
+        for t in range(T - 1, -1, -1):
+            st[t] = x
+            x = self._bps[t, x]
+        return st[::2]
+
     def cnn_probs(self, which, mspec_local, ranges, edge_left, edge_right):
         net, nmel = self.nets[which]
         m = mspec_local.numpy()[:, :nmel]
@@ -85,13 +137,14 @@ def _specs():
     return Spec(so.VAD_SMN), Spec(so.GENDER)
 
 
-def _worker(rank, world, port, s16, q):
+def _worker(rank, world, port, s16, q, energy_mode='auto'):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
     try:
         torch.set_num_threads(2)
         plan = ShardPlan(len(s16), world)
+        plan.energy_mode = energy_mode
         sa, sb = plan.sample_range(rank)
         vad, gender = _specs()
         comm = Comm('cpu')
@@ -133,8 +186,8 @@ def test_shard_plan_arithmetic():
         ShardPlan(16000 * 5, 8)
 
 
-@pytest.mark.parametrize('world', [2, 3])
-def test_sharded_equals_unsharded_gloo(world):
+@pytest.mark.parametrize('world,energy_mode', [(2, 'replicated'), (2, 'transfer'), (3, 'auto')])
+def test_sharded_equals_unsharded_gloo(world, energy_mode):
     from oracle import cnn_oracle, segmenter_oracle as so
     s16 = synth_audio(50, seed=21)
     mods = _mods()
@@ -147,7 +200,7 @@ def test_sharded_equals_unsharded_gloo(world):
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, s16, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, s16, q, energy_mode)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=600) for _ in range(world)]

@@ -22,7 +22,7 @@ def _mods():
             'gender': models.synthetic_keras_cnn(24, 2, seed=13, width=0.5)}
 
 
-def _worker(rank, world, port, s16, backend, q):
+def _worker(rank, world, port, s16, backend, q, energy_mode='auto'):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dev = rank if backend == 'nccl' else 0
@@ -34,7 +34,7 @@ def _worker(rank, world, port, s16, backend, q):
         seg = Segmenter(vad_engine='smn', detect_gender=True, ffmpeg=None, models=_mods(), device=dev)
         plan = ShardPlan(len(s16), world)
         sa, sb = plan.sample_range(rank)
-        segs, comm = segment_signal_sharded(seg, s16[sa:sb], len(s16))
+        segs, comm = segment_signal_sharded(seg, s16[sa:sb], len(s16), energy_mode=energy_mode)
         ref = seg.segment_signal(s16) if rank == 0 else None
         q.put((rank, segs, ref, comm.bytes))
     finally:
@@ -49,12 +49,12 @@ def _free_port():
     return p
 
 
-def _run(world, backend):
+def _run(world, backend, energy_mode='auto'):
     s16 = synth_audio(120, seed=33)
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, s16, backend, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, s16, backend, q, energy_mode)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=900) for _ in range(world)], key=lambda t: t[0])
@@ -67,10 +67,12 @@ def _run(world, backend):
         assert segs == ref, (rank, segs[:4], ref[:4])
 
 
-def test_sharded_two_ranks_one_gpu_gloo():
+@pytest.mark.parametrize('world,energy_mode', [(2, 'replicated'), (2, 'transfer'), (3, 'transfer')])
+def test_sharded_ranks_one_gpu_gloo(world, energy_mode):
+    """`transfer` = the whole-file energy chain cut at rank boundaries (max-plus transfer matrices)."""
     if not torch.cuda.is_available():
         pytest.skip('no CUDA device')
-    _run(2, 'gloo')
+    _run(world, 'gloo', energy_mode)
 
 
 def test_sharded_nccl_one_rank_per_gpu():
