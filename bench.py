@@ -308,7 +308,7 @@ def run_b200(args):
                    'networks': 'synthetic-weight stand-ins of the ~1.4M-parameter CNN family (release .hdf5 absent)',
                    'fft': args.fft, 'l2': 'inputs larger than L2 (%.2f GB PCM per step)' % (pcm.numel() * 2 / 1e9),
                    'parallelism': ('single GPU' if world == 1 else
-                                   'one %g h recording time-sharded over %d GPUs (34-frame halo); NCCL all-gather of loge and CNN posteriors, Viterbi replicated' % (args.hours * world, world)),
+                                   'one %g h recording time-sharded over %d GPUs (34-frame halo); NCCL all-gathers of loge, CNN posteriors, label tracks and (>= 3 ranks) max-plus transfer matrices of the energy Viterbi' % (args.hours * world, world)),
                    'segments': len(segs),
                    'vad_flops_per_patch': seg.vad.nn.flops_per_patch, 'gender_flops_per_patch': seg.gender.nn.flops_per_patch},
         'clocks': clk,
