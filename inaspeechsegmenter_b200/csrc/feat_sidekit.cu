@@ -132,7 +132,7 @@ sidekit_features_kernel(const void *__restrict__ pcm, int64_t n_samples, int64_t
                 v = (T)y * S.win[n];
             }
             // z[m] = v[2m] + i v[2m+1]
-            if (n & 1) im[skew(n >> 1)] = v; else re[skew(n >> 1)] = v;
+            if (n & 1) im[skewT<T>(n >> 1)] = v; else re[skewT<T>(n >> 1)] = v;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
@@ -145,7 +145,7 @@ sidekit_features_kernel(const void *__restrict__ pcm, int64_t n_samples, int64_t
         for (int i = 0; i < 9; ++i) {
             const int k = lane + 32 * i;
             if (k <= 256) {
-                const int ka = skew(k & 255), kb = skew((256 - k) & 255);
+                const int ka = skewT<T>(k & 255), kb = skewT<T>((256 - k) & 255);
                 const T zr = re[ka], zi = im[ka];
                 const T cr = re[kb], ci = -im[kb];                  // conj(Z[256-k])
                 const T er = (T)0.5 * (zr + cr), ei = (T)0.5 * (zi + ci);

@@ -119,7 +119,7 @@ vbx_fbank_kernel(const void *__restrict__ pcm, const double *__restrict__ dither
                 const double xp = (k == 0) ? xc : (x[k - 1] - mean);
                 v = __dsub_rn(xc, __dmul_rn(xp, 0.97)) * S.win[k];
             }
-            if (k & 1) im[skew(k >> 1)] = v; else re[skew(k >> 1)] = v;
+            if (k & 1) im[skewT<double>(k >> 1)] = v; else re[skewT<double>(k >> 1)] = v;
         }
         __syncwarp();
         warp_fft256<double>(re, im, S.tw256, lane);
@@ -127,7 +127,7 @@ vbx_fbank_kernel(const void *__restrict__ pcm, const double *__restrict__ dither
         for (int i = 0; i < 9; ++i) {
             const int k = lane + 32 * i;
             if (k <= 256) {
-                const int ka = skew(k & 255), kb = skew((256 - k) & 255);
+                const int ka = skewT<double>(k & 255), kb = skewT<double>((256 - k) & 255);
                 const double zr = re[ka], zi = im[ka];
                 const double cr = re[kb], ci = -im[kb];
                 const double er = 0.5 * (zr + cr), ei = 0.5 * (zi + ci);

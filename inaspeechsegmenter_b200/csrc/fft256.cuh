@@ -4,7 +4,10 @@
 // followed by the even/odd split X[k] = E[k] + W512^k O[k].
 #pragma once
 
+// skew by one element per 128 bytes: every 32 floats / every 16 doubles
 __device__ __forceinline__ int skew(int i) { return i + (i >> 5); }
+template <typename T>
+__device__ __forceinline__ int skewT(int i) { return sizeof(T) == 8 ? i + (i >> 4) : i + (i >> 5); }
 
 // One radix-4 Stockham pass set over a warp-private 256-point complex buffer.
 template <typename T>
@@ -23,7 +26,7 @@ __device__ __forceinline__ void warp_fft256(T *re, T *im, const T *tw, int lane)
             T vr[4], vi[4];
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-                const int idx = skew(j + 64 * t);
+                const int idx = skewT<T>(j + 64 * t);
                 const T xr = re[idx], xi = im[idx];
                 if (t == 0 || s == 0) { vr[t] = xr; vi[t] = xi; }
                 else {
@@ -47,7 +50,7 @@ __device__ __forceinline__ void warp_fft256(T *re, T *im, const T *tw, int lane)
         for (int b = 0; b < 2; ++b)
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-                const int idx = skew(j0[b] + t * Ns);
+                const int idx = skewT<T>(j0[b] + t * Ns);
                 re[idx] = yr[b][t];
                 im[idx] = yi[b][t];
             }

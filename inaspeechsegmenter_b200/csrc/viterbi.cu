@@ -106,7 +106,8 @@ viterbi_forward_kernel(const float *__restrict__ src, const double *__restrict__
                     for (int k = 1; k < K; ++k) {
                         const double c = V[k] + prm.A[k][j];
                         const double vc = es[j] + c;            // speculative: same op whichever wins
-                        const bool u = better(c, best);
+                        // energy emissions / transitions are finite constants: V can never be NaN there
+                        const bool u = ENERGY ? (c > best) : better(c, best);
                         best = u ? c : best;
                         vn = u ? vc : vn;
                         arg = u ? (unsigned)k : arg;

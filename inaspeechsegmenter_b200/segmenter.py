@@ -216,8 +216,7 @@ class Segmenter:
             loge = torch.from_numpy(host).to(self.ctx.device)
         stats = getattr(loge, '_iss_stats', None)
         if stats is None:
-            fin = torch.isfinite(loge)
-            stats = torch.stack((loge[fin].double().sum(), fin.sum().double()))
+            stats = engine.loge_stats(self.ctx, loge)          # same reduction kernel/order as the fused one in K1
         track = engine.energy_viterbi(self.ctx, loge, stats, self.energy_ratio, out_stride=2).cpu().numpy()
         return [('noEnergy' if lab == 0 else 'energy', a, b) for lab, a, b in _rle(track)]
 
