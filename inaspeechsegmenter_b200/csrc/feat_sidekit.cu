@@ -16,6 +16,7 @@
 // which is the reference's own precision recipe (sidekit_mfcc.py:231-233).
 #include <math.h>
 #include <string.h>
+#include <type_traits>
 
 #include "iss_common.cuh"
 
@@ -24,10 +25,10 @@ namespace {
 #include "fft256.cuh"
 
 
-constexpr int FR = 64;                               // frames per CTA tile
+constexpr int FR = 48;                               // frames per CTA tile (int16 staging + 48 frames => 3 CTAs/SM in fp64 mode)
 constexpr int NWARP = 8;
 constexpr int NTHREAD = NWARP * 32;
-constexpr int TILE_SAMPLES = (FR - 1) * ISS_HOP + ISS_WIN;   // 10480
+constexpr int TILE_SAMPLES = (FR - 1) * ISS_HOP + ISS_WIN;   // 7920
 constexpr int ZPAD = 272;                            // 257 + skew, padded
 
 
@@ -45,9 +46,10 @@ template <> struct Tab<double> {
     static __device__ __forceinline__ float log_(double x) { return (float)log(x); }
 };
 
-template <typename T>
+template <typename T, int PCM>
 struct Smem {
-    float samples[TILE_SAMPLES];
+    // staged verbatim: int16 PCM stays 2 bytes/sample in shared memory and is scaled by 1/32768 on use
+    typename std::conditional<PCM == ISS_PCM_S16, int16_t, float>::type samples[TILE_SAMPLES + 8];
     T win[ISS_WIN];
     T tw256[512];
     T tw512[2 * 257 + 2];
@@ -60,13 +62,13 @@ struct Smem {
 };
 
 template <typename T, int PCM>
-__global__ void __launch_bounds__(NTHREAD, 2)
+__global__ void __launch_bounds__(NTHREAD, 3)
 sidekit_features_kernel(const void *__restrict__ pcm, int64_t n_samples, int64_t n_frames,
                         const SidekitTables *__restrict__ tabs, float *__restrict__ mspec,
                         float *__restrict__ loge, double *__restrict__ partials, int vec_ok)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem<T> &S = *reinterpret_cast<Smem<T> *>(smem_raw);
+    Smem<T, PCM> &S = *reinterpret_cast<Smem<T, PCM> *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t f0 = (int64_t)blockIdx.x * FR;
     const int64_t s0 = f0 * ISS_HOP;
@@ -82,32 +84,27 @@ sidekit_features_kernel(const void *__restrict__ pcm, int64_t n_samples, int64_t
 
     if (PCM == ISS_PCM_S16) {
         const int16_t *p = reinterpret_cast<const int16_t *>(pcm) + s0;
-        if (vec_ok) {                                  // 8 samples per 16-byte load
+        int16_t *dst = reinterpret_cast<int16_t *>(S.samples);
+        if (vec_ok) {                                  // 8 samples per 16-byte load (tile offsets are multiples of 15360 B)
             const int nv = nsamp >> 3;
             const int4 *pv = reinterpret_cast<const int4 *>(p);
-            for (int i = tid; i < nv; i += NTHREAD) {
-                const int4 v = __ldg(pv + i);
-                const int w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    S.samples[8 * i + 2 * q] = (float)(short)(w[q] & 0xffff) * (1.0f / 32768.0f);
-                    S.samples[8 * i + 2 * q + 1] = (float)(short)(w[q] >> 16) * (1.0f / 32768.0f);
-                }
-            }
-            for (int i = (nv << 3) + tid; i < nsamp; i += NTHREAD) S.samples[i] = (float)p[i] * (1.0f / 32768.0f);
+            int4 *dv = reinterpret_cast<int4 *>(dst);
+            for (int i = tid; i < nv; i += NTHREAD) dv[i] = __ldg(pv + i);
+            for (int i = (nv << 3) + tid; i < nsamp; i += NTHREAD) dst[i] = p[i];
         } else {
-            for (int i = tid; i < nsamp; i += NTHREAD) S.samples[i] = (float)p[i] * (1.0f / 32768.0f);
+            for (int i = tid; i < nsamp; i += NTHREAD) dst[i] = p[i];
         }
     } else {
         const float *p = reinterpret_cast<const float *>(pcm) + s0;
+        float *dst = reinterpret_cast<float *>(S.samples);
         if (vec_ok) {
             const int nv = nsamp >> 2;
             const float4 *pv = reinterpret_cast<const float4 *>(p);
-            float4 *sv = reinterpret_cast<float4 *>(S.samples);
+            float4 *sv = reinterpret_cast<float4 *>(dst);
             for (int i = tid; i < nv; i += NTHREAD) sv[i] = __ldg(pv + i);
-            for (int i = (nv << 2) + tid; i < nsamp; i += NTHREAD) S.samples[i] = p[i];
+            for (int i = (nv << 2) + tid; i < nsamp; i += NTHREAD) dst[i] = p[i];
         } else {
-            for (int i = tid; i < nsamp; i += NTHREAD) S.samples[i] = p[i];
+            for (int i = tid; i < nsamp; i += NTHREAD) dst[i] = p[i];
         }
     }
     __syncthreads();
@@ -117,7 +114,10 @@ sidekit_features_kernel(const void *__restrict__ pcm, int64_t n_samples, int64_t
     double acc_sum = 0.0, acc_cnt = 0.0;
 
     for (int fl = warp; fl < nfr; fl += NWARP) {
-        const float *x = S.samples + fl * ISS_HOP;
+        const auto *xs = S.samples + fl * ISS_HOP;
+        auto x = [&](int n) -> float {
+            return (PCM == ISS_PCM_S16) ? (float)xs[n] * (1.0f / 32768.0f) : (float)xs[n];
+        };
         // ---- pre-emphasis (f32, numpy op order: x - (x_prev * 0.97f)), energy, window ----
         double e = 0.0;
 #pragma unroll
@@ -125,8 +125,8 @@ sidekit_features_kernel(const void *__restrict__ pcm, int64_t n_samples, int64_t
             const int n = lane + 32 * i;                 // 0..511
             T v = (T)0;
             if (n < ISS_WIN) {
-                const float xc = x[n];
-                const float xp = (n == 0) ? xc : x[n - 1];
+                const float xc = x(n);
+                const float xp = (n == 0) ? xc : x(n - 1);
                 const float y = __fsub_rn(xc, __fmul_rn(xp, 0.97f));
                 e += (double)y * (double)y;
                 v = (T)y * S.win[n];
@@ -316,7 +316,7 @@ static int launch_features(iss_ctx *ctx, const void *d_pcm, int64_t n_samples, i
                            float *d_mspec, float *d_loge, int vec_ok, cudaStream_t st)
 {
     auto kern = sidekit_features_kernel<T, PCM>;
-    const size_t smem = sizeof(Smem<T>);
+    const size_t smem = sizeof(Smem<T, PCM>);
     ISS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)ntiles, NTHREAD, smem, st>>>(d_pcm, n_samples, L, ctx->d_tables, d_mspec, d_loge,
                                                    ctx->d_partials, vec_ok);

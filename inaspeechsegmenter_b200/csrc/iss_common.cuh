@@ -30,7 +30,7 @@ constexpr int ISS_HOP = 160;
 constexpr int ISS_NFFT = 512;
 constexpr int ISS_NBIN = 257;
 constexpr int ISS_NMEL = 24;
-constexpr int ISS_FB_MAXNNZ = 1024;
+constexpr int ISS_FB_MAXNNZ = 512;     // trfbank(16000,512,100,8000,0,24) has 454 non-zeros
 
 struct SidekitTables {
     // sparse mel filterbank: filter m covers bins [lo[m], lo[m]+cnt[m]) with weights w[off[m]..]
