@@ -169,3 +169,20 @@ def test_cli_parser_matches_reference_flags():
     from inaspeechsegmenter_b200 import cli
     a = cli.build_parser().parse_args(['-i', 'x.wav', '-o', '/tmp', '-d', 'sm', '-g', 'false', '-b', 'None', '-e', 'textgrid', '-r', '0.05', '-s', '1024'])
     assert (a.vad_engine, a.detect_gender, a.ffmpeg_binary, a.export_format, a.energy_ratio, a.batch_size) == ('sm', 'false', 'None', 'textgrid', 0.05, 1024)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU port of the reference path) prints ONE JSON line with the contract keys."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '1',
+                          '--cpu-sample-sec', '4'], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith('{')][-1]
+    d = json.loads(line)
+    for k in ('impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+              'vs_baseline', 'dtype', 'data', 'config', 'cpu_baseline', 'e2e'):
+        assert k in d, k
+    assert d['impl'] == 'reference' and d['value'] > 0 and d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['value'] == d['value']
