@@ -393,10 +393,11 @@ conv_gemm_tc_kernel(const ConvArgs a)
 //     ring), which removes them from the producers' critical path;
 //   * operand A goes registers -> TMEM (tcgen05.st) into an ST-deep ring next to the two
 //     accumulators, so shared memory only carries B for the MMAs.
-template <int BN, int DA, int SB, int ST>
+template <int BN, int DA, int SB, int ST, int NSETS = 1>
 struct Tc2Cfg {
     static constexpr int A_SLOT = 4096;                                  // 32 rows x 128 B per warp
-    static constexpr int A_RING = 4 * DA * A_SLOT;
+    static constexpr int A_RING = 4 * NSETS * DA * A_SLOT;
+    static constexpr int THREADS = 32 * (4 * NSETS + 1);
     static constexpr int B_TILE = BN * TBK * 4;
     static constexpr int B_STAGE = 2 * B_TILE;                           // hi | lo
     static constexpr int SMEM = A_RING + SB * B_STAGE + 1024 + 256;
@@ -412,11 +413,16 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int BN, int DA, int SB, int ST>
-__global__ void __launch_bounds__(160, (Tc2Cfg<BN, DA, SB, ST>::TMEM_COLS <= 256 ? 2 : 1))
+// NSETS = 2: one CTA per SM with TWO producer warp-sets (warps 0-3 and 5-8; a warp's TMEM lane
+// quadrant is warp_id % 4) that alternate k-blocks, and a TMEM A ring as deep as 512 columns allow.
+// The micro-benchmark (tools/umma_microbench.cu, profiles/r01_umma_microbench.txt) shows one issuing
+// thread saturates the tensor pipe with this MMA pattern, so the limit is how decoupled producers
+// and issuer are, not the number of issuers.
+template <int BN, int DA, int SB, int ST, int NSETS>
+__global__ void __launch_bounds__(32 * (4 * NSETS + 1), (Tc2Cfg<BN, DA, SB, ST, NSETS>::TMEM_COLS <= 256 ? 2 : 1))
 conv_gemm_tc2_kernel(const ConvArgs a)
 {
-    using Cfg = Tc2Cfg<BN, DA, SB, ST>;
+    using Cfg = Tc2Cfg<BN, DA, SB, ST, NSETS>;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     unsigned char *b_ring = smem;                                        // 1024-aligned operand tiles first
@@ -445,8 +451,11 @@ conv_gemm_tc2_kernel(const ConvArgs a)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {
+    if (warp != 4) {
         // ============================ A producers ============================
+        const int quad = warp & 3;                           // TMEM lane quadrant this warp may access
+        const int pset = (warp < 4) ? 0 : 1;                 // producer set: handles k-blocks kb % NSETS == pset
+        const int pwarp = pset * 4 + quad;                   // index of this warp's private ring
         // Issue-slot budget matters here (the kernel is instruction-issue bound before it is tensor
         // bound): per-row state is 32-bit and precomputed, the filter tap advances incrementally
         // (no integer division in the loop) and un-padded convolutions skip all bounds checks.
@@ -457,7 +466,7 @@ conv_gemm_tc2_kernel(const ConvArgs a)
         uint32_t ok_mask = 0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int64_t m = m0 + warp * 32 + 4 * i + sub;
+            const int64_t m = m0 + quad * 32 + 4 * i + sub;
             const bool okr = m < a.M;
             ok_mask |= (okr ? 1u : 0u) << i;
             const int64_t mm = okr ? m : 0;
@@ -471,15 +480,24 @@ conv_gemm_tc2_kernel(const ConvArgs a)
             row_dst[i] = (uint32_t)(rl * 128 + ((chunk ^ (rl & 7)) << 4));
         }
         const bool padded = (a.PT | a.PL) != 0 || (a.OH - 1) * a.SH + a.KH > a.H || (a.OW - 1) * a.SW + a.KW > a.W;
-        unsigned char *my_ring = a_ring + warp * DA * Cfg::A_SLOT;
+        unsigned char *my_ring = a_ring + pwarp * DA * Cfg::A_SLOT;
         const uint32_t ring_u32 = smem_u32(my_ring);
-        // incremental tap state of the NEXT k-block to issue
-        int is_c0 = 0, is_ss = 0, is_rr = 0, is_kb = 0;
+        // incremental tap state of the NEXT k-block this set issues (k-blocks pset, pset+NSETS, ...)
+        int is_c0 = 0, is_ss = 0, is_rr = 0, is_kb = 0, is_n = 0;
         uint32_t is_off = 0;                                 // (rr*W + ss)*C + c0
         const uint32_t wrap_step = (uint32_t)((a.W - a.KW) * a.C + TBK);
+        auto advance = [&]() {
+            ++is_kb;
+            is_c0 += TBK; is_off += TBK;
+            if (is_c0 == a.C) {
+                is_c0 = 0;
+                if (++is_ss == a.KW) { is_ss = 0; ++is_rr; is_off += wrap_step - TBK; }
+            }
+        };
+        for (int q = 0; q < pset; ++q) advance();
         auto issue_a = [&]() {
             if (is_kb < nkb) {
-                const uint32_t slot = ring_u32 + (uint32_t)(is_kb % DA) * Cfg::A_SLOT;
+                const uint32_t slot = ring_u32 + (uint32_t)(is_n % DA) * Cfg::A_SLOT;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     bool ok = (ok_mask >> i) & 1u;
@@ -490,18 +508,15 @@ conv_gemm_tc2_kernel(const ConvArgs a)
                     const float *src = a.in + (ok ? (uint32_t)(row_base[i] + is_off) : 0u);
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(slot + row_dst[i]), "l"(src), "r"(ok ? 16 : 0) : "memory");
                 }
-                ++is_kb;
-                is_c0 += TBK; is_off += TBK;
-                if (is_c0 == a.C) {
-                    is_c0 = 0;
-                    if (++is_ss == a.KW) { is_ss = 0; ++is_rr; is_off += wrap_step - TBK; }
-                }
+                ++is_n;
+#pragma unroll
+                for (int q = 0; q < NSETS; ++q) advance();
             }
             cp_async_commit();
         };
 #pragma unroll
         for (int p = 0; p < DA; ++p) issue_a();
-        const uint32_t lane_addr = ((uint32_t)(warp * 32)) << 16;
+        const uint32_t lane_addr = ((uint32_t)(quad * 32)) << 16;
         uint32_t lds_off[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) lds_off[j] = (uint32_t)(lane * 128 + ((j ^ (lane & 7)) << 4));
@@ -509,10 +524,10 @@ conv_gemm_tc2_kernel(const ConvArgs a)
         // read and split while they drain; only then tcgen05.wait::st + arrive.  The per-warp critical
         // path per k-block is max(store latency, load+split) instead of their sum.
         uint32_t hi[32], lo[32];
-        auto load_split = [&](int kb) {
+        auto load_split = [&](int n) {                        // n-th k-block of this set
             cp_async_wait<DA - 1>();
             __syncwarp();
-            const unsigned char *slot = my_ring + (kb % DA) * Cfg::A_SLOT;
+            const unsigned char *slot = my_ring + (n % DA) * Cfg::A_SLOT;
             uint32_t v[32];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -527,15 +542,16 @@ conv_gemm_tc2_kernel(const ConvArgs a)
                 lo[j] = __float_as_uint(__uint_as_float(v[j]) - __uint_as_float(hi[j]));
             }
         };
-        load_split(0);
-        for (int kb = 0; kb < nkb; ++kb) {
+        if (pset < nkb) load_split(0);
+        int nloc = 0;
+        for (int kb = pset; kb < nkb; kb += NSETS, ++nloc) {
             const int st = kb % ST;
             mbar_wait(&emptyA[st], ((kb / ST) & 1) ^ 1, 1);
             tc_fence_after();
             const uint32_t ta = tmem_base + lane_addr + Cfg::ACC_COLS + st * 2 * TBK;
             tmem_st32(ta, hi);
             tmem_st32(ta + TBK, lo);
-            if (kb + 1 < nkb) load_split(kb + 1);            // overlaps the TMEM store latency
+            if (kb + NSETS < nkb) load_split(nloc + 1);       // overlaps the TMEM store latency
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             mbar_arrive(&fullA[st]);
@@ -549,7 +565,7 @@ conv_gemm_tc2_kernel(const ConvArgs a)
         const bool has_bias = a.flags & ISS_F_BIAS, pre = a.flags & ISS_F_AFFINE_PRE, post = a.flags & ISS_F_AFFINE_POST;
         const bool relu = a.flags & ISS_F_RELU, resid = a.flags & ISS_F_RESIDUAL;
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
+        for (int c = pset * 32; c < BN; c += 32 * NSETS) {     // the sets share the columns
             uint32_t acc[32];
             {
                 uint32_t corr[32];
@@ -575,7 +591,7 @@ conv_gemm_tc2_kernel(const ConvArgs a)
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int rl = 4 * i + sub;
-                const int64_t m = m0 + warp * 32 + rl;
+                const int64_t m = m0 + quad * 32 + rl;
                 const uint4 q4 = *reinterpret_cast<const uint4 *>(stage_buf + rl * 128 + ((chunk ^ (rl & 7)) << 4));
                 if (m < a.M) {
                     float y[4] = {__uint_as_float(q4.x), __uint_as_float(q4.y), __uint_as_float(q4.z), __uint_as_float(q4.w)};
@@ -656,11 +672,11 @@ conv_gemm_tc2_kernel(const ConvArgs a)
     }
 }
 
-template <int BN, int DA, int SB, int ST>
+template <int BN, int DA, int SB, int ST, int NSETS = 1>
 int launch_tc2(const ConvArgs &a, cudaStream_t st)
 {
-    using Cfg = Tc2Cfg<BN, DA, SB, ST>;
-    auto kern = conv_gemm_tc2_kernel<BN, DA, SB, ST>;
+    using Cfg = Tc2Cfg<BN, DA, SB, ST, NSETS>;
+    auto kern = conv_gemm_tc2_kernel<BN, DA, SB, ST, NSETS>;
     static bool configured = false;
     if (!configured) {
         ISS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
@@ -669,7 +685,7 @@ int launch_tc2(const ConvArgs &a, cudaStream_t st)
     const int64_t gm = (a.M + TBM - 1) / TBM;
     ISS_REQUIRE(gm < (1ll << 31), ISS_ERR_INVALID, "conv_tc: M too large");
     dim3 grid((unsigned)gm, (unsigned)(a.N / BN));
-    kern<<<grid, 160, Cfg::SMEM, st>>>(a);
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(a);
     ISS_CUDA_OK(cudaGetLastError());
     iss_count_launch();
     return ISS_OK;
@@ -728,6 +744,11 @@ int iss_launch_conv_tc(const ConvArgs &a, int mode, cudaStream_t st)
     // BN: the widest of {256,128,64,32} dividing N
     // two accumulators per tile (main + correction) => BN <= 128 (2 x 128 + A ring <= 512 TMEM columns)
     if (ts) {
+        static const int two_sets = [] { const char *e = getenv("ISS_B200_TC_SETS"); return (e && e[0] == '2') ? 1 : 0; }();
+        if (two_sets) {
+            if (a.N % 128 == 0) return launch_tc2<128, 2, 4, 4, 2>(a, st);   // 193 KB smem, 512 TMEM cols
+            if (a.N % 64 == 0) return launch_tc2<64, 3, 4, 6, 2>(a, st);     // 161 KB smem, 512 TMEM cols
+        }
         if (a.N % 128 == 0) return launch_tc2<128, 4, 4, 4>(a, st);      // 193 KB smem, 512 TMEM cols (2x128 acc + 4 A stages), 1 CTA/SM
         if (a.N % 64 == 0) return launch_tc2<64, 3, 3, 2>(a, st);        //  97 KB smem, 256 TMEM cols, 2 CTAs/SM
         return launch_tc2<32, 3, 4, 3>(a, st);                            //  81 KB smem, 256 TMEM cols
