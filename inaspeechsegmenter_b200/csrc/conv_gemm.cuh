@@ -22,6 +22,7 @@ struct ConvArgs {
     const int32_t *row0; const float *mu; const float *sigma;
     // tensor-core path: weights transposed + split, [N][Kp] each (nullptr => fp32 CUDA-core kernel)
     const float *wt_hi; const float *wt_lo; const float *wt_tiled; int Kp;
+    int debug_same_addr;    // timing experiment only (ISS_B200_TC_DEBUG=1): every gather hits the same 128 bytes
 };
 
 #define ISS_GEMM_FP32  0      /* fp32 CUDA cores (conv_gemm.cu) */

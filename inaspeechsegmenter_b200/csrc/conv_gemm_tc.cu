@@ -505,8 +505,12 @@ conv_gemm_tc2_kernel(const ConvArgs a)
                         const int ih = row_ih0[i] + is_rr, iw = row_iw0[i] + is_ss;
                         ok = ok && ih >= 0 && ih < a.H && iw >= 0 && iw < a.W;
                     }
-                    const float *src = a.in + (ok ? (uint32_t)(row_base[i] + is_off) : 0u);
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(slot + row_dst[i]), "l"(src), "r"(ok ? 16 : 0) : "memory");
+                    const float *src = a.in + (ok ? ((a.debug_same_addr & 1) ? (uint32_t)(chunk * 4) : (uint32_t)(row_base[i] + is_off)) : 0u);
+                    // .cg (L2 only) by default; L1-allocating gathers (.ca, experiment bit 2) measured no different
+                    if (a.debug_same_addr & 2)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(slot + row_dst[i]), "l"(src), "r"(ok ? 16 : 0) : "memory");
+                    else
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(slot + row_dst[i]), "l"(src), "r"(ok ? 16 : 0) : "memory");
                 }
                 ++is_n;
 #pragma unroll
@@ -738,8 +742,11 @@ bool iss_conv_tc_eligible(const ConvArgs &a)
     return a.wt_hi && a.wt_lo && a.wt_tiled && a.Kp > 0 && a.C % 32 == 0 && a.K % 32 == 0 && a.N % 32 == 0 && a.N >= 32;
 }
 
-int iss_launch_conv_tc(const ConvArgs &a, int mode, cudaStream_t st)
+int iss_launch_conv_tc(const ConvArgs &a_in, int mode, cudaStream_t st)
 {
+    static const int dbg = [] { const char *e = getenv("ISS_B200_TC_DEBUG"); return e ? atoi(e) : 0; }();   // timing experiments: 1 = same-address gathers, 2 = L1-allocating gathers
+    ConvArgs a = a_in;
+    a.debug_same_addr = dbg;
     const bool ts = (mode == ISS_GEMM_TC_TS);
     // BN: the widest of {256,128,64,32} dividing N
     // two accumulators per tile (main + correction) => BN <= 128 (2 x 128 + A ring <= 512 TMEM columns)
@@ -747,7 +754,7 @@ int iss_launch_conv_tc(const ConvArgs &a, int mode, cudaStream_t st)
         static const int two_sets = [] { const char *e = getenv("ISS_B200_TC_SETS"); return (e && e[0] == '2') ? 1 : 0; }();
         if (two_sets) {
             if (a.N % 128 == 0) return launch_tc2<128, 2, 4, 4, 2>(a, st);   // 193 KB smem, 512 TMEM cols
-            if (a.N % 64 == 0) return launch_tc2<64, 3, 4, 6, 2>(a, st);     // 161 KB smem, 512 TMEM cols
+            if (a.N % 64 == 0) return launch_tc2<64, 2, 4, 6, 2>(a, st);     // 129 KB smem (=> ~96 KB L1), 512 TMEM cols
         }
         if (a.N % 128 == 0) return launch_tc2<128, 4, 4, 4>(a, st);      // 193 KB smem, 512 TMEM cols (2x128 acc + 4 A stages), 1 CTA/SM
         if (a.N % 64 == 0) return launch_tc2<64, 3, 3, 2>(a, st);        //  97 KB smem, 256 TMEM cols, 2 CTAs/SM

@@ -315,3 +315,76 @@ def test_cli_with_hdf5_models(rt, synth_models, media, tmp_path, monkeypatch):
     got = (out / 'musanmix.csv').read_text().splitlines()
     ref = open(os.path.join(media, 'musanmix-smn-gender.csv')).read().splitlines()
     assert got[0] == ref[0] and [l for l in got if l.startswith('noEnergy')] == [l for l in ref if l.startswith('noEnergy')]
+
+
+def _alt_keras_cnn(nmel, n_classes, seed):
+    """A second architecture exercising the rest of the layer interpreter: 'same' padding, strides,
+    'same' max-pooling with odd sizes, activation fused in the Conv2D config, Dense -> ReLU -> BatchNorm
+    (affine AFTER the activation), bias-free convolution, BatchNorm without scale."""
+    rng = np.random.default_rng(seed)
+    L, W = [], {}
+
+    def conv(name, kh, kw, cin, cout, strides, padding, act, bias=True):
+        W[name + '/kernel'] = (rng.standard_normal((kh, kw, cin, cout)) * np.sqrt(2.0 / (kh * kw * cin))).astype(np.float32)
+        if bias:
+            W[name + '/bias'] = rng.normal(0, 0.05, cout).astype(np.float32)
+        L.append({'class_name': 'Conv2D', 'config': {'name': name, 'filters': cout, 'kernel_size': [kh, kw], 'strides': strides,
+                                                      'padding': padding, 'use_bias': bias, 'activation': act}})
+
+    def bn(name, ch, scale=True):
+        if scale:
+            W[name + '/gamma'] = rng.uniform(0.8, 1.2, ch).astype(np.float32)
+        W[name + '/beta'] = rng.normal(0, 0.1, ch).astype(np.float32)
+        W[name + '/moving_mean'] = rng.normal(0, 0.2, ch).astype(np.float32)
+        W[name + '/moving_variance'] = rng.uniform(0.5, 1.5, ch).astype(np.float32)
+        L.append({'class_name': 'BatchNormalization', 'config': {'name': name, 'axis': -1, 'epsilon': 1e-3, 'center': True, 'scale': scale}})
+
+    L.append({'class_name': 'InputLayer', 'config': {'name': 'in', 'batch_input_shape': [None, 68, nmel, 1]}})
+    conv('c1', 3, 3, 1, 32, [1, 1], 'same', 'relu')                       # first layer with padding (direct kernel, padded)
+    conv('c2', 3, 3, 32, 64, [2, 1], 'same', 'linear', bias=False)        # stride 2 in time, asymmetric 'same' padding, TC path
+    bn('b2', 64, scale=False)
+    L.append({'class_name': 'Activation', 'config': {'name': 'a2', 'activation': 'relu'}})
+    L.append({'class_name': 'MaxPooling2D', 'config': {'name': 'p2', 'pool_size': [3, 2], 'strides': [2, 2], 'padding': 'same'}})
+    conv('c3', 1, 1, 64, 96, [1, 1], 'valid', 'relu')                     # 1x1, N = 96 (32-wide TC tiles)
+    L.append({'class_name': 'MaxPooling2D', 'config': {'name': 'p3', 'pool_size': [2, 2], 'strides': None, 'padding': 'valid'}})
+    L.append({'class_name': 'Flatten', 'config': {'name': 'f'}})
+    h, w = 68, nmel
+    h, w = -(-h // 2), w                    # c2 stride (2,1) same
+    h, w = -(-h // 2), -(-w // 2)           # p2 same
+    h, w = h // 2, w // 2                   # p3 valid
+    fin = h * w * 96
+    W['d1/kernel'] = (rng.standard_normal((fin, 64)) * np.sqrt(2.0 / fin)).astype(np.float32)
+    W['d1/bias'] = rng.normal(0, 0.05, 64).astype(np.float32)
+    L.append({'class_name': 'Dense', 'config': {'name': 'd1', 'units': 64, 'use_bias': True, 'activation': 'relu'}})
+    bn('bd1', 64)                                                          # BatchNorm AFTER the activation
+    L.append({'class_name': 'Dropout', 'config': {'name': 'do', 'rate': 0.5}})
+    W['d2/kernel'] = (rng.standard_normal((64, n_classes)) * np.sqrt(1.0 / 64)).astype(np.float32)
+    W['d2/bias'] = rng.normal(0, 0.05, n_classes).astype(np.float32)
+    L.append({'class_name': 'Dense', 'config': {'name': 'd2', 'units': n_classes, 'use_bias': True, 'activation': 'linear'}})
+    L.append({'class_name': 'Activation', 'config': {'name': 'sm', 'activation': 'softmax'}})
+    return {'class_name': 'Sequential', 'config': {'name': 'alt', 'layers': L}}, W
+
+
+@pytest.mark.parametrize('mode', [0, 2])
+@pytest.mark.parametrize('nmel', [21, 24])
+def test_k2_layer_interpreter_alt_architecture(rt, nmel, mode):
+    """The release networks' architecture is unknown here, so the generic layer interpreter is
+    checked on a second, deliberately different Keras config (padding/stride/pool/BN-order variants)."""
+    from oracle import sidekit_oracle as sk
+    lib = rt['lib'].load()
+    prev = lib.iss_get_gemm_mode()
+    try:
+        lib.iss_set_gemm_mode(mode)
+        cfg, w = _alt_keras_cnn(nmel, 3, seed=nmel)
+        sig = synth_audio(25, seed=29).astype(np.float32) / np.float32(32768)
+        mspec, loge = sk.logmel_loge(sig)
+        P = (len(loge) + 1) // 2
+        ranges = [(0, 50), (200, 460), (P - 40, P)]
+        ref = _oracle_probs(cfg, w, mspec, nmel, ranges)
+        net = rt['engine'].CnnModel.from_keras(rt['ctx'], cfg, w, nmel)
+        got = net.forward(torch.from_numpy(mspec).cuda(), ranges).cpu().numpy()
+        err = np.abs(got - ref).max()
+        REPORT['k2_alt_arch_nmel%d_mode%d' % (nmel, mode)] = dict(softmax_max_abs=float(err))
+        assert got.shape == ref.shape and err <= 1e-4, err
+    finally:
+        lib.iss_set_gemm_mode(prev)
