@@ -8,22 +8,14 @@
 //      A.B ~= Ah.Bh + Ah.Bl + Al.Bh          (dropped Al.Bl ~ 2^-22 relative)
 // i.e. three kind::tf32 MMAs per K-step into the same fp32 TMEM accumulator.
 //
-// Tile: 128 output positions (UMMA_M = 128, cta_group::1) x BN output channels, K in
-// blocks of 32 floats (= one 128-byte swizzle row).  Roles per CTA (160 threads):
-//   warps 0-3  producers: thread r owns A row r: im2col gather of 32 contiguous
-//              channels of one filter tap (NHWC => one 128-byte global segment), exact
-//              hi/lo split in registers, then
-//                SS mode: st.shared in the canonical K-major SWIZZLE_128B layout;
-//                TS mode: tcgen05.st straight into TMEM (A never touches shared
-//                         memory, which is the bottleneck resource for narrow-N tiles);
-//              plus the pre-split, pre-transposed weight tile [BN][32] into smem.
-//              After the K loop the same warps run the epilogue: tcgen05.ld of their
-//              32-lane TMEM quadrant, bias -> BN affine -> (+residual) -> ReLU -> affine,
-//              float4 stores.
-//   warp 4     TMEM allocator + single-thread MMA issuer; tcgen05.commit releases the
-//              smem/TMEM stage back to the producers and finally signals the epilogue.
-// Two CTAs fit per SM (<= 113 KB smem, 256 TMEM columns each) so one CTA's epilogue
-// overlaps the other's main loop.
+// Two kernels live here:
+//   conv_gemm_tc2_kernel  (engine 2, the default): A operand registers -> TMEM (tcgen05.st), weights as
+//       one bulk copy per stage of host-pre-swizzled tiles, two accumulators (main + correction),
+//       asynchronous cp.async gather ring.  See the block comment above that kernel and DESIGN.md 4.1.
+//   conv_gemm_tc_kernel   (engine 1, kept as the all-shared-memory comparison point): both operands in
+//       the canonical K-major SWIZZLE_128B smem layout, producers split hi/lo into two A tiles.
+// Tile: 128 output positions (UMMA_M = 128, cta_group::1) x BN output channels, K in blocks of 32 floats
+// (= one 128-byte swizzle row); 4 producer/epilogue warps + 1 TMEM-allocator / MMA-issuer warp.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>

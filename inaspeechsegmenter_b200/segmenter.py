@@ -67,6 +67,8 @@ def feats_from_signal(sig, device=0, fft_precision=_lib.FFT_FP64, ctx_name='feat
     else:
         pcm = _to_device_pcm(sig, dev)
     fe = _get_frontend(ctx_name, device)
+    if pcm.numel() < 400:
+        raise ValueError('media %s holds %d samples: less than one 25 ms analysis frame' % (medianame, pcm.numel()))
     mspec, loge, stats = fe(pcm, fft_precision)
     difflen = 0
     if len(loge) < PATCH_W:
