@@ -73,6 +73,11 @@ SIGNATURES = {
     'iss_resnet_flops_per_window': (_d, [_vp, _i]),
     'iss_resnet_workspace_bytes': (_i64, [_vp, _i, _i]),
     'iss_resnet_embed': (_i, [_vp, _vp, _vp, _i64, _vp, _i, _i, _vp, _vp, _i64, _vp]),
+    'iss_mlp_create': (_i, [_vp, _c.POINTER(LayerDesc), _i, _vp, _i64, _i, _c.POINTER(_vp)]),
+    'iss_mlp_destroy': (_i, [_vp]),
+    'iss_mlp_out_dim': (_i, [_vp]),
+    'iss_mlp_workspace_bytes': (_i64, [_vp, _i64]),
+    'iss_mlp_forward': (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp]),
     'iss_cnn_profile': (_i, [_vp, _i]),
     'iss_cnn_profile_read': (_i, [_vp, _c.POINTER(_d), _c.POINTER(_i64), _c.POINTER(_d)]),
     'iss_cnn_layer_flops': (_d, [_vp, _i]),

@@ -103,6 +103,46 @@ class CnnModel:
             pass
 
 
+class MlpModel:
+    """Dense stack on device: the ``keras.Model.predict`` seam of the gender-detection MLP
+    (vbx_segmenter.py:116-124,188-191)."""
+
+    def __init__(self, ctx, config, weights, in_dim):
+        self.ctx = ctx
+        low = lower_keras_model(config, weights, 1, in_dim, allow_no_head=True)
+        self.lowered = low
+        blob = np.ascontiguousarray(low.blob, dtype=np.float32)
+        h = ctypes.c_void_p()
+        _lib.check(_lib.load().iss_mlp_create(ctx.handle, low.c_descs(), len(low.descs), _lib.ptr(blob), blob.size,
+                                              in_dim, ctypes.byref(h)), 'iss_mlp_create')
+        self.handle, self.in_dim = h, in_dim
+        self.out_dim = _lib.load().iss_mlp_out_dim(h)
+
+    def predict(self, x, **_):
+        """x: [n, in_dim] numpy or CUDA tensor -> numpy float32 [n, out_dim] (keras predict contract)."""
+        t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+        t = t.to(self.ctx.device).contiguous()
+        n = t.shape[0]
+        y = torch.empty((n, self.out_dim), dtype=torch.float32, device=self.ctx.device)
+        if n:
+            lib = _lib.load()
+            work = self.ctx.workspace('mlp', lib.iss_mlp_workspace_bytes(self.handle, n))
+            _lib.check(lib.iss_mlp_forward(self.ctx.handle, self.handle, _lib.ptr(t), n, _lib.ptr(y), _lib.ptr(work),
+                                           work.numel(), _stream_ptr(self.ctx.device)), 'iss_mlp_forward')
+        return y.cpu().numpy()
+
+    def close(self):
+        if self.handle:
+            _lib.load().iss_mlp_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 # ---- Viterbi operators (pyannote_viterbi.py:118-224 + viterbi_utils.py:29-49) ------------
 
 def log_trans_exp(exp, cost0=0, cost1=0):

@@ -57,7 +57,7 @@ class LoweredModel:
         return arr
 
 
-def lower_keras_model(config, weights, in_h, in_w):
+def lower_keras_model(config, weights, in_h, in_w, allow_no_head=False):
     """Keras Sequential config (dict / JSON) + weights -> LoweredModel.
 
     Supported layers: InputLayer, Conv2D, BatchNormalization, Activation /
@@ -196,7 +196,7 @@ def lower_keras_model(config, weights, in_h, in_w):
             cur = None
         else:
             raise NotImplementedError('Keras layer %s is not supported by the B200 CNN operator' % cls)
-    if not (h == 1 and w == 1):
+    if not (h == 1 and w == 1) and not (allow_no_head and flat):
         raise NotImplementedError('model must end in a Dense head')
     return LoweredModel(descs, np.concatenate(blob) if blob else np.zeros(0, np.float32), in_h, in_w, c,
                         config, weights)

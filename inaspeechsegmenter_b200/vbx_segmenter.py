@@ -5,8 +5,9 @@
 ``B200BackendExtractor`` is a drop-in for ``OnnxBackendExtractor``: same
 ``get_embedding(fea[T,64]) -> [256]`` and ``__call__(basename, fea, duration)``
 contract, but ``__call__`` embeds all windows in batches on the GPU instead of
-one ONNX call per 0.24 s of audio.  ``VoiceFemininityScoring``'s pyannote/MLP
-glue (:92-202) is downstream of the x-vectors and out of scope.
+one ONNX call per 0.24 s of audio.  ``VoiceFemininityScoring`` (:92-202, SURVEY
+N3) is mirrored at the end of the file: the MLP runs on device (``iss_mlp_*``),
+the pyannote interval bookkeeping is restated in plain Python.
 """
 import ctypes
 import logging
@@ -255,3 +256,110 @@ class B200BackendExtractor(VBxExtractor):
                 else:
                     out.append((key, (round(start / 100.0, 3), round(duration, 3)), x))
         return [(key, seg, x * 10) for key, seg, x in out]
+
+
+# ------------------------------------------------------------------ VoiceFemininityScoring (vbx_segmenter.py:28-202)
+def _overlap(start, stop, speech):
+    """Total duration of [start, stop] covered by the (disjoint) speech intervals: what
+    ``Timeline([Segment(start, stop)]).crop(vad_timeline).duration()`` yields (:140)."""
+    return sum(max(0.0, min(stop, e) - max(start, b)) for b, e in speech)
+
+
+def is_mid_speech(start, stop, speech):
+    """True if the window's midpoint lies strictly inside a speech segment (:28-37)."""
+    m = (start + stop) / 2
+    return any(b < m < e for b, e in speech)
+
+
+def add_needed_vectors(xvectors, t_mid):
+    """Keep at least 50 % of the windows whose midpoint is in speech (:40-52): when the
+    overlap threshold removed too many, the windows are taken back in decreasing overlap order."""
+    min_pred = round(0.5 * len(t_mid))
+    if len(xvectors) < min_pred:
+        order = np.argsort(np.array([t[0] for t in t_mid], dtype=np.float64))[::-1]
+        ranked = [t_mid[i] for i in order]
+        diff = min_pred - len(xvectors)
+        for _, k, (s0, s1), x in ranked[len(xvectors):len(xvectors) + diff]:
+            xvectors.append((k, (s0, s1), x))
+    return xvectors
+
+
+def get_femininity_score(g_preds):
+    """Share of retained windows predicted feminine (p >= 0.5) (:55-61).  The reference goes through a
+    pyannote Annotation keyed by segment, so a later window with identical bounds replaces an earlier one."""
+    by_segment = {}
+    for start, stop, p in g_preds:
+        by_segment[(start, stop)] = bool(np.all(np.asarray(p) >= 0.5))
+    return sum(by_segment.values()) / len(by_segment)
+
+
+class VoiceFemininityScoring:
+    """Same contract as the reference class (vbx_segmenter.py:92-202): ``__call__(fpath) ->
+    (score, speech_duration, nb_vectors)``.  VAD = the B200 ``Segmenter('smn', detect_gender=False)``,
+    x-vectors = K4 + K5, the gender MLP runs on device through ``iss_mlp_forward``; the interval
+    bookkeeping the reference delegates to pyannote.core is plain Python here.
+    Extra optional arguments: ``device``, ``ffmpeg`` and ``models`` = {'vad': (config, weights),
+    'mlp': (config, weights), 'resnet': state_dict} to bypass the model-file lookup."""
+
+    def __init__(self, gd_model_criteria="bgc", backend='onnx', device=0, ffmpeg='ffmpeg', models=None):
+        assert backend in ['onnx', 'b200'], "Backend should be 'onnx' (served by the B200 extractor) or 'b200'."
+        from .engine import MlpModel
+        from .models import find_model_file, load_model_file
+        from .segmenter import Segmenter
+        models = models or {}
+        assert gd_model_criteria in ["bgc", "vfp"], "Gender detection model Criteria must be 'bgc' (default) or 'vfp'"
+        if gd_model_criteria == "bgc":
+            gd_model, self.vad_thresh = "interspeech2023_all.hdf5", 0.7
+        else:
+            gd_model, self.vad_thresh = "interspeech2023_cvfr.hdf5", 0.62
+        self.vad = Segmenter(vad_engine='smn', detect_gender=False, ffmpeg=ffmpeg, device=device,
+                             models={'vad': models['vad']} if 'vad' in models else None)
+        self.ctx = self.vad.ctx
+        self.xvector_model = B200BackendExtractor(state_dict=models.get('resnet'), ctx=self.ctx)
+        mlp = models.get('mlp')
+        if mlp is None:
+            path = find_model_file(gd_model)
+            if path is None:
+                raise FileNotFoundError('%s not found (reference asset, remote_utils.py:4-15)' % gd_model)
+            mlp = load_model_file(path)
+        self.gender_detection_mlp_model = MlpModel(self.ctx, mlp[0], mlp[1], EMBED_DIM)
+        self.frontend = VbxFrontEnd(self.ctx)
+        self.ffmpeg = ffmpeg
+
+    def apply_vad(self, xvectors, speech):
+        """vbx_segmenter.py:129-145 with `speech` = [(start, end)] of the 'speech' VAD segments."""
+        midpoint_seg, kept = [], []
+        for key, (start, stop), x in xvectors:
+            if is_mid_speech(start, stop, speech):
+                ratio = _overlap(start, stop, speech) / (stop - start)
+                if ratio >= self.vad_thresh:
+                    kept.append((key, (start, stop), x))
+                midpoint_seg.append((ratio, key, (start, stop), x))
+        return add_needed_vectors(kept, midpoint_seg)
+
+    def score_signal(self, sig, basename='signal'):
+        """The body of __call__ on a decoded 16 kHz mono signal (numpy int16 / float)."""
+        sig = np.asarray(sig)
+        duration = len(sig) / SR
+        vad_seg = self.vad.segment_signal(sig if sig.dtype in (np.int16, np.float32) else sig.astype(np.float32))
+        speech = [(b, e) for lab, b, e in vad_seg if lab == 'speech']
+        speech_duration = sum(e - b for b, e in speech)
+        if not speech_duration:
+            return None, speech_duration, 0
+        pcm = torch.from_numpy(np.ascontiguousarray(sig if sig.dtype == np.int16 else sig.astype(np.float32))).to(self.ctx.device)
+        features = self.frontend(pcm)
+        x_vectors = self.xvector_model(basename, features, duration)
+        x_vectors = self.apply_vad(x_vectors, speech)
+        x = np.asarray([x for _, _, x in x_vectors])
+        gender_pred = self.gender_detection_mlp_model.predict(x, verbose=0)
+        if len(gender_pred) > 1:
+            gender_pred = np.squeeze(gender_pred)
+        g = [(seg[0], seg[1], p) for (_, seg, _), p in zip(x_vectors, gender_pred)]
+        return get_femininity_score(g), speech_duration, len(g)
+
+    def __call__(self, fpath):
+        """Voice femininity score of a media file (vbx_segmenter.py:147-202)."""
+        from .io import media2sig16kmono
+        basename = os.path.splitext(os.path.basename(fpath))[0]
+        sig = media2sig16kmono(fpath, ffmpeg=self.ffmpeg, dtype='float32', return_int16=True)
+        return self.score_signal(sig, basename)

@@ -35,6 +35,7 @@ extern "C" {
 typedef struct iss_ctx iss_ctx;
 typedef struct iss_cnn iss_cnn;
 typedef struct iss_resnet iss_resnet;
+typedef struct iss_mlp iss_mlp;
 
 /* ---- library / context ------------------------------------------------- */
 
@@ -242,6 +243,19 @@ int64_t iss_resnet_workspace_bytes(const iss_resnet *net, int n_windows, int win
 int iss_resnet_embed(iss_ctx *ctx, iss_resnet *net, const float *d_fea, int64_t M,
                      const int32_t *h_win_start, int n_windows, int win_len, float *d_emb,
                      void *d_work, int64_t work_bytes, void *stream);
+
+/* ---- Dense stack applied to x-vectors ------------------------------------------------
+ * Replaces gender_detection_mlp_model.predict(x) of VoiceFemininityScoring
+ * (inaSpeechSegmenter/vbx_segmenter.py:116-124,188-191).  layers: ISS_LAYER_DENSE records
+ * only (flags as for the CNN head, ISS_F_SIGMOID supported, no softmax). */
+int iss_mlp_create(iss_ctx *ctx, const iss_layer_desc *layers, int n_layers, const float *h_blob,
+                   int64_t blob_len, int in_dim, iss_mlp **out);
+int iss_mlp_destroy(iss_mlp *mlp);
+int iss_mlp_out_dim(const iss_mlp *mlp);
+int64_t iss_mlp_workspace_bytes(const iss_mlp *mlp, int64_t n_rows);
+/* d_x: float32 [n_rows][in_dim]; d_y: float32 [n_rows][out_dim]. */
+int iss_mlp_forward(iss_ctx *ctx, iss_mlp *mlp, const float *d_x, int64_t n_rows, float *d_y,
+                    void *d_work, int64_t work_bytes, void *stream);
 
 /* Live roofline support: record CUDA events around every launch of layer
  * `layer` (index into the iss_layer_desc list; -1 switches profiling off) on

@@ -136,3 +136,75 @@ def test_vbx_extractor_call_vs_oracle(vctx, golden):
     scale = max(np.abs(x).max() for _, _, x in ref)
     for (_, _, a), (_, _, b) in zip(got, ref):
         assert np.abs(a - b).max() <= 2e-4 * scale
+
+
+def _synthetic_mlp(seed=3):
+    rng = np.random.default_rng(seed)
+    L, W = [{'class_name': 'InputLayer', 'config': {'name': 'in', 'batch_input_shape': [None, 256]}}], {}
+    dims = [256, 128, 64, 1]
+    for i in range(3):
+        n = 'dense_%d' % i
+        W[n + '/kernel'] = (rng.standard_normal((dims[i], dims[i + 1])) * np.sqrt(1.0 / dims[i])).astype(np.float32)
+        W[n + '/bias'] = rng.normal(0, 0.1, dims[i + 1]).astype(np.float32)
+        L.append({'class_name': 'Dense', 'config': {'name': n, 'units': dims[i + 1], 'use_bias': True,
+                                                    'activation': 'sigmoid' if i == 2 else 'relu'}})
+        if i == 0:
+            b = 'bn_0'
+            W[b + '/gamma'] = rng.uniform(0.8, 1.2, 128).astype(np.float32); W[b + '/beta'] = rng.normal(0, 0.1, 128).astype(np.float32)
+            W[b + '/moving_mean'] = rng.normal(0, 0.1, 128).astype(np.float32); W[b + '/moving_variance'] = rng.uniform(0.5, 1.5, 128).astype(np.float32)
+            L.append({'class_name': 'BatchNormalization', 'config': {'name': b, 'axis': -1, 'epsilon': 1e-3}})
+        if i < 2:
+            L.append({'class_name': 'Dropout', 'config': {'name': 'do_%d' % i, 'rate': 0.3}})
+    return {'class_name': 'Sequential', 'config': {'name': 'mlp', 'layers': L}}, W
+
+
+def test_vfs_glue_matches_oracle_cpu():
+    """Interval bookkeeping of VoiceFemininityScoring (no GPU): product helpers vs the oracle restatement."""
+    from inaspeechsegmenter_b200 import vbx_segmenter as vb
+    from oracle import vfs_oracle
+    rng = np.random.default_rng(5)
+    vad = [('noEnergy', 0.0, 1.0), ('speech', 1.0, 4.2), ('music', 4.2, 6.0), ('speech', 6.0, 6.9), ('noise', 6.9, 9.0), ('speech', 9.0, 12.0)]
+    xv = [('k%d' % i, (round(i * 0.24, 3), round(i * 0.24 + 1.44, 3)), rng.standard_normal(256).astype(np.float32)) for i in range(44)]
+    cfg, w = _synthetic_mlp()
+    mlp = lambda x: vfs_oracle.mlp_numpy(cfg, w, x)                       # noqa: E731
+    for thresh in (0.62, 0.7, 0.99):
+        ref = vfs_oracle.femininity(vad, xv, mlp, thresh)
+
+        class Fake:
+            vad_thresh = thresh
+        speech = [(b, e) for lab, b, e in vad if lab == 'speech']
+        kept = vb.VoiceFemininityScoring.apply_vad(Fake, list(xv), speech)
+        p = mlp(np.asarray([x for _, _, x in kept]))
+        p = np.squeeze(p) if len(p) > 1 else p
+        got = (vb.get_femininity_score([(s[0], s[1], pi) for (_, s, _), pi in zip(kept, p)]), sum(e - b for b, e in speech), len(kept))
+        assert got[0] == ref[0] and abs(got[1] - ref[1]) < 1e-12 and got[2] == ref[2], (thresh, got, ref)
+
+
+@gpu
+def test_vfs_end_to_end_vs_oracle(vctx, synth_models):
+    """VoiceFemininityScoring on a synthetic clip: VAD + K4 + K5 + device MLP + glue == oracle pipeline."""
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from conftest import synth_audio
+    from inaspeechsegmenter_b200 import vbx_segmenter as vb
+    from oracle import cnn_oracle, segmenter_oracle as so, vbx_oracle as vx, vfs_oracle
+    import warnings
+    sd = vx.synthetic_resnet101_state(seed=5)
+    cfg, w = _synthetic_mlp()
+    s16 = synth_audio(30, seed=42)
+    vfs = vb.VoiceFemininityScoring('vfp', ffmpeg=None, models={'vad': synth_models['smn'], 'mlp': (cfg, w), 'resnet': sd})
+    got = vfs.score_signal(s16, 'clip')
+    # oracle pipeline
+    mspec, loge, difflen = so.media2feats(s16.astype(np.float32) / np.float32(32768))
+    v = so.DnnSegmenterOracle(cnn_oracle.KerasLikeModel(*synth_models['smn']), **so.VAD_SMN)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        vad_seg = so.segment_feats(mspec, loge, difflen, 0, v, None)
+    fea = vx.get_features(s16.astype(np.float64) / 32768.0)
+    xv = vx.extract_xvectors(fea, vx.ResNet101Oracle(sd, threads=8), 'clip', len(s16) / 16000)
+    ref = vfs_oracle.femininity(vad_seg, xv, lambda x: vfs_oracle.mlp_numpy(cfg, w, x), 0.62)
+    assert got[2] == ref[2] and abs(got[1] - ref[1]) < 1e-9, (got, ref)
+    assert got[0] == ref[0] or (got[0] is not None and abs(got[0] - ref[0]) <= 1.0 / max(ref[2], 1)), (got, ref)
+    # device MLP vs numpy on the same inputs
+    x = np.asarray([x for _, _, x in xv])
+    assert np.abs(vfs.gender_detection_mlp_model.predict(x) - vfs_oracle.mlp_numpy(cfg, w, x)).max() <= 1e-5
