@@ -23,6 +23,11 @@ struct ConvArgs {
     // tensor-core path: weights transposed + split, [N][Kp] each (nullptr => fp32 CUDA-core kernel)
     const float *wt_hi; const float *wt_lo; const float *wt_tiled; int Kp;
     int debug_same_addr;    // timing experiment only (ISS_B200_TC_DEBUG=1): every gather hits the same 128 bytes
+    // slab kernel (conv_gemm_tc3_kernel) only, filled in by iss_launch_conv_tc
+    int slab_R;             // output rows (of width OW) per 128-row GEMM tile
+    int slab_rows;          // input rows the slab is sized for
+    int64_t in_elems;       // floats in `in` (loads past the end are zero-filled)
+    unsigned long long *prof;   // ISS_B200_TC_PROF=1: per-role wait-cycle counters (experiments only)
 };
 
 #define ISS_GEMM_FP32  0      /* fp32 CUDA cores (conv_gemm.cu) */

@@ -17,6 +17,7 @@
 // Tile: 128 output positions (UMMA_M = 128, cta_group::1) x BN output channels, K in blocks of 32 floats
 // (= one 128-byte swizzle row); 4 producer/epilogue warps + 1 TMEM-allocator / MMA-issuer warp.
 #include <cuda.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
@@ -376,6 +377,93 @@ conv_gemm_tc_kernel(const ConvArgs a)
 }
 
 
+
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t p;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
+    return p != 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// B loader + MMA issuer, run by ALL 32 lanes of warp 4 with warp-uniform control flow; only the
+// tcgen05 / bulk-copy instructions themselves sit under elect.sync.  This matters more than anything
+// else in the kernel: with the loop inside `if (lane == 0)` ptxas cannot prove the tcgen05 operands
+// (TMEM addresses, smem descriptors) warp-uniform and wraps EVERY tcgen05.mma in an
+// ELECT / 4 x R2UR.BROADCAST / BRA.U.ANY "waterfall" -- ~50 issue cycles per MMA, ~330 instructions per
+// k-block on one thread, i.e. 600-1100 cycles per k-block against a tensor-time floor of 392 (measured with
+// the what-if switches of ISS_B200_TC_DEBUG: removing all MMAs saved 12 %, removing everything but
+// the issue loop skeleton still cost 60 % of the run time).  With uniform control flow and the TMEM base
+// passed through REDUX (a uniform-register producer) the 8 MMAs of a k-block are 8 back-to-back UTCHMMA.
+// The weights are static, so the host stores them already tiled and swizzled exactly as the smem operand
+// image ([n-tile][k-block][hi|lo][BN x 128 B, SWIZZLE_128B]); one stage is a single 1-D bulk copy.
+template <int BN, int SB, int ST, int B_STAGE, uint32_t ACC_COLS>
+__device__ __forceinline__ void tc_issuer_warp(const ConvArgs &a, uint32_t tmem_base_any, unsigned char *b_ring, uint64_t *fullA,
+                                               uint64_t *emptyA, uint64_t *fullB, uint64_t *emptyB, uint64_t *accum, int nkb)
+{
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+    constexpr uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+    const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, tmem_base_any);
+    const unsigned char *wt = reinterpret_cast<const unsigned char *>(a.wt_tiled) + (size_t)blockIdx.y * nkb * B_STAGE;
+    const bool dbg_nob = a.debug_same_addr & 8, dbg_nomma = a.debug_same_addr & 16, dbg_nocommit_b = a.debug_same_addr & 32;   // timing experiments
+    auto issue_b = [&](int kb) {
+        if (kb < nkb) {
+            const int sl = kb % SB;
+            if (elect_one()) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&fullB[sl])), "r"((uint32_t)B_STAGE) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(smem_u32(b_ring + sl * B_STAGE)), "l"(wt + (size_t)kb * B_STAGE),
+                               "r"((uint32_t)B_STAGE), "r"(smem_u32(&fullB[sl])) : "memory");
+            }
+            __syncwarp();
+        }
+    };
+    for (int p = 0; p < SB - 1 + (dbg_nob ? 1 : 0); ++p) issue_b(p);
+    const uint32_t d_main = tmem_base, d_lo = tmem_base + BN;
+    const bool prof = a.prof != nullptr;
+    long long w_b = 0, w_a = 0, w_e = 0;
+    const long long t_i0 = prof ? clock64() : 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+        const int st = kb % ST, sl = kb % SB;
+        const long long c0 = prof ? clock64() : 0;
+        if (!dbg_nob || kb < SB) mbar_wait(&fullB[sl], (kb / SB) & 1, 2);
+        const long long c1 = prof ? clock64() : 0;
+        mbar_wait(&fullA[st], (kb / ST) & 1, 3);
+        if (prof) { w_b += c1 - c0; w_a += clock64() - c1; }
+        tc_fence_after();
+        const uint64_t dbh = make_sw128_desc(smem_u32(b_ring + sl * B_STAGE));
+        const uint32_t ta = tmem_base + ACC_COLS + st * 2 * TBK;
+        if (elect_one()) {
+            // the B stage is [hi rows | lo rows] and the accumulators are [D_main | D_lo] in adjacent TMEM
+            // columns, hence Ah.Bh and Ah.Bl are ONE MMA of width 2*BN (D_main += Ah.Bh, D_lo += Ah.Bl);
+            // Al.Bh follows into D_lo.
+#pragma unroll
+            for (int kk = 0; kk < TBK / 8; ++kk) {
+                const uint32_t first = (kb > 0 || kk > 0) ? 1u : 0u;
+                if (dbg_nomma && first) continue;
+                umma_tf32_ts(d_main, ta + kk * 8, dbh + 2 * kk, idesc2, first);          // Ah.[Bh | Bl]
+                umma_tf32_ts(d_lo, ta + TBK + kk * 8, dbh + 2 * kk, idesc, 1u);          // Al.Bh
+            }
+            umma_commit(&emptyA[st]);
+            if (!dbg_nocommit_b) umma_commit(&emptyB[sl]);
+            if (kb == nkb - 1) umma_commit(accum);
+        }
+        __syncwarp();
+        // refill the slot of k-block kb-1 with kb+SB-1: its MMAs retire before those just issued start,
+        // so this wait is short and the tensor pipe is never drained
+        if (kb + SB - 1 < nkb && !dbg_nob) {
+            const long long c2 = prof ? clock64() : 0;
+            if (kb >= 1) mbar_wait(&emptyB[(kb - 1) % SB], ((kb - 1) / SB) & 1, 4);   // slot (kb-1)%SB; unused so far when kb == 0
+            if (prof) w_e += clock64() - c2;
+            issue_b(kb + SB - 1);
+        }
+    }
+    if (prof && (threadIdx.x & 31) == 0) {
+        atomicAdd(a.prof + 0, (unsigned long long)(clock64() - t_i0)); atomicAdd(a.prof + 1, (unsigned long long)w_b);
+        atomicAdd(a.prof + 2, (unsigned long long)w_a); atomicAdd(a.prof + 3, (unsigned long long)w_e);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Asynchronous TS pipeline (the production path).  Differences from the kernel above:
 //   * A rows are fetched with cp.async (16-byte, L2 -> smem, zero-fill for padding / tail rows)
@@ -400,6 +488,10 @@ struct Tc2Cfg {
 __device__ __forceinline__ void cp_async16(void *dst, const void *src, int src_bytes)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async16_u32(uint32_t dst, const void *src, int src_bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -429,7 +521,7 @@ conv_gemm_tc2_kernel(const ConvArgs a)
     const int nkb = a.Kp / TBK;
 
     if (tid == 0) {
-        for (int s = 0; s < ST; ++s) { mbar_init(&fullA[s], 128); mbar_init(&emptyA[s], 1); }
+        for (int s = 0; s < ST; ++s) { mbar_init(&fullA[s], 4); mbar_init(&emptyA[s], 1); }
         for (int s = 0; s < SB; ++s) { mbar_init(&emptyB[s], 1); mbar_init(&fullB[s], 1); }
         mbar_init(accum, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -542,7 +634,8 @@ conv_gemm_tc2_kernel(const ConvArgs a)
         int nloc = 0;
         for (int kb = pset; kb < nkb; kb += NSETS, ++nloc) {
             const int st = kb % ST;
-            mbar_wait(&emptyA[st], ((kb / ST) & 1) ^ 1, 1);
+            if (lane == 0) mbar_wait(&emptyA[st], ((kb / ST) & 1) ^ 1, 1);   // one poller / one arrival per warp:
+            __syncwarp();                                                     // 128 threads hammering the mbarriers cost more than the MMAs
             tc_fence_after();
             const uint32_t ta = tmem_base + lane_addr + Cfg::ACC_COLS + st * 2 * TBK;
             tmem_st32(ta, hi);
@@ -550,12 +643,14 @@ conv_gemm_tc2_kernel(const ConvArgs a)
             if (kb + NSETS < nkb) load_split(nloc + 1);       // overlaps the TMEM store latency
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
-            mbar_arrive(&fullA[st]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&fullA[st]);
         }
         cp_async_wait<0>();
 
         // ============================ epilogue ============================
-        mbar_wait(accum, 0, 5);
+        if (lane == 0) mbar_wait(accum, 0, 5);
+        __syncwarp();
         tc_fence_after();
         unsigned char *stage_buf = my_ring;                  // the A ring is idle now: reuse slot 0 as transpose buffer
         const bool has_bias = a.flags & ISS_F_BIAS, pre = a.flags & ISS_F_AFFINE_PRE, post = a.flags & ISS_F_AFFINE_POST;
@@ -609,56 +704,8 @@ conv_gemm_tc2_kernel(const ConvArgs a)
         }
         tc_fence_before();
     } else {
-        // ============================ B loader + MMA issuer (one thread) ============================
-        // The weights are static, so the host stores them already tiled and swizzled exactly as the
-        // smem operand image ([n-tile][k-block][hi|lo][BN x 128 B, SWIZZLE_128B]); one stage is then a
-        // single 1-D bulk copy (async proxy, completes on an mbarrier) instead of BN*16 cp.async.
-        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
-        constexpr uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
-        if (lane == 0) {
-            const unsigned char *wt = reinterpret_cast<const unsigned char *>(a.wt_tiled) +
-                                      (size_t)blockIdx.y * nkb * Cfg::B_STAGE;
-            auto issue_b = [&](int kb) {
-                if (kb < nkb) {
-                    const int sl = kb % SB;
-                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&fullB[sl])), "r"((uint32_t)Cfg::B_STAGE) : "memory");
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"(smem_u32(b_ring + sl * Cfg::B_STAGE)), "l"(wt + (size_t)kb * Cfg::B_STAGE),
-                                   "r"((uint32_t)Cfg::B_STAGE), "r"(smem_u32(&fullB[sl])) : "memory");
-                }
-            };
-            for (int p = 0; p < SB - 1; ++p) issue_b(p);
-            const uint32_t d_main = tmem_base, d_lo = tmem_base + BN;
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int st = kb % ST, sl = kb % SB;
-                mbar_wait(&fullB[sl], (kb / SB) & 1, 2);
-                mbar_wait(&fullA[st], (kb / ST) & 1, 3);
-                tc_fence_after();
-                const uint32_t bs = smem_u32(b_ring + sl * Cfg::B_STAGE);
-                const uint64_t dbh = make_sw128_desc(bs);
-                // The kernel is bound by the issue rate of this one thread, so instructions are made as
-                // large as possible: the B stage is [hi rows | lo rows] and the accumulators are
-                // [D_main | D_lo] in adjacent TMEM columns, hence Ah.Bh and Ah.Bl are ONE MMA of width
-                // 2*BN (D_main += Ah.Bh, D_lo += Ah.Bl); Al.Bh follows into D_lo.
-#pragma unroll
-                for (int kk = 0; kk < TBK / 8; ++kk) {
-                    const uint32_t first = (kb > 0 || kk > 0) ? 1u : 0u;
-                    const uint32_t ta = tmem_base + Cfg::ACC_COLS + st * 2 * TBK + kk * 8;
-                    umma_tf32_ts(d_main, ta, dbh + 2 * kk, idesc2, first);                // Ah.[Bh | Bl]
-                    umma_tf32_ts(d_lo, ta + TBK, dbh + 2 * kk, idesc, 1u);                // Al.Bh
-                }
-                umma_commit(&emptyA[st]);
-                umma_commit(&emptyB[sl]);
-                if (kb == nkb - 1) umma_commit(accum);
-                // refill the slot of k-block kb-1 with kb+SB-1: its MMAs retire before those just
-                // issued start, so this wait is short and the tensor pipe is never drained
-                if (kb + SB - 1 < nkb) {
-                    if (kb >= 1) mbar_wait(&emptyB[(kb - 1) % SB], ((kb - 1) / SB) & 1, 4);   // slot (kb-1)%SB; unused so far when kb == 0
-                    issue_b(kb + SB - 1);
-                }
-            }
-        }
-        __syncwarp();
+        // ============================ B loader + MMA issuer (warp 4) ============================
+        tc_issuer_warp<BN, SB, ST, Cfg::B_STAGE, Cfg::ACC_COLS>(a, tmem_base, b_ring, fullA, emptyA, fullB, emptyB, accum, nkb);
         tc_fence_before();
     }
     __syncthreads();
@@ -666,6 +713,307 @@ conv_gemm_tc2_kernel(const ConvArgs a)
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
     }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Slab variant of the TS pipeline for un-padded stride-1 convolutions with KH*KW > 1 (the CNN's
+// 5x4 / 3x3 layers).  The im2col gathers of conv_gemm_tc2_kernel re-read every input element
+// KH*KW times from L2 (ncu: 17.9 GB of L2->SM traffic per launch of the 64->64 5x4 layer, 9 TB/s,
+// i.e. ~3/4 of the measured L2 throughput cap) -- here the input rows a tile needs are brought into
+// shared memory ONCE (coalesced cp.async, pixel-swizzled so that the lane = GEMM-row reads are
+// bank-conflict free) and every filter tap is served from that slab.
+//   tile = R = 128 / OW consecutive output rows of the global row sequence q = img * OH + oh
+//   slab = input rows g(q0) .. g(q1) + KH - 1 with g(q) = q + (q / OH) * (KH - 1): one contiguous range
+//          of the NHWC tensor even when the tile straddles images
+//   GEMM row r <-> (q0 + r / OW, r % OW); output offset = q0 * OW + r (contiguous)
+// Everything downstream of the A fetch (hi/lo split, tcgen05.st ring, B bulk stages, MMA issue,
+// epilogue) is the tc2 design.
+template <int BN, int SB, int ST, int NSETS = 1>
+struct Tc3Cfg {
+    static constexpr int THREADS = 32 * (4 * NSETS + 1);
+    static constexpr int PRODUCERS = 128 * NSETS;
+    static constexpr int B_TILE = BN * TBK * 4;
+    static constexpr int B_STAGE = 2 * B_TILE;
+    static constexpr uint32_t ACC_COLS = 2 * BN;
+    static constexpr uint32_t TMEM_COLS = tmem_cols_pow2(ACC_COLS + ST * 2 * TBK);
+    static constexpr int FIXED = SB * B_STAGE + 1024 + 256;              // + slab bytes
+};
+
+// NSETS = 2: two producer warp-sets (warps 0-3 and 5-8, TMEM lane quadrant = warp % 4) alternate k-blocks.
+template <int BN, int SB, int ST, int NSETS>
+__global__ void __launch_bounds__(32 * (4 * NSETS + 1), (Tc3Cfg<BN, SB, ST, NSETS>::TMEM_COLS <= 256 ? 2 : 1))
+conv_gemm_tc3_kernel(const ConvArgs a)
+{
+    using Cfg = Tc3Cfg<BN, SB, ST, NSETS>;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    unsigned char *b_ring = smem;
+    unsigned char *slab = smem + SB * Cfg::B_STAGE;
+    const int slab_bytes = a.slab_rows * a.W * a.C * 4 < 32768 ? 32768 : a.slab_rows * a.W * a.C * 4;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(slab + slab_bytes);
+    uint64_t *fullA = bars, *emptyA = bars + ST, *emptyB = bars + 2 * ST, *fullB = bars + 2 * ST + SB, *accum = bars + 2 * ST + 2 * SB;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * ST + 2 * SB + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n0 = blockIdx.y * BN;
+    const int nkb = a.Kp / TBK;
+    const int R = a.slab_R, KH1 = a.KH - 1;
+    const int64_t Q = a.M / a.OW;                                // output rows in the whole batch
+    const int64_t q0 = (int64_t)blockIdx.x * R;
+    const int64_t mbase = q0 * a.OW;
+    const int nq = (int)((Q - q0) < (int64_t)R ? (Q - q0) : (int64_t)R);
+    const int valid = nq * a.OW;                                 // GEMM rows of this tile that exist
+    const int64_t img0 = q0 / a.OH;
+
+    if (tid == 0) {
+        for (int s = 0; s < ST; ++s) { mbar_init(&fullA[s], 4); mbar_init(&emptyA[s], 1); }   // 4 = the warps of ONE producer set
+        for (int s = 0; s < SB; ++s) { mbar_init(&emptyB[s], 1); mbar_init(&fullB[s], 1); }
+        mbar_init(accum, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp != 4) {
+        // ============================ slab fill (128 threads) ============================
+        const int quad = warp & 3;                               // TMEM lane quadrant this warp may access
+        const int pset = (warp < 4) ? 0 : 1;                     // producer set: k-blocks kb % NSETS == pset
+        const int ptid = pset * 128 + quad * 32 + lane;          // 0 .. PRODUCERS-1
+        const bool prof = a.prof != nullptr && ptid == 0;
+        long long t_start = prof ? clock64() : 0, t_wait = 0, t_fill = 0, t_loop = 0, t_acc = 0;
+        const uint32_t slab_u32 = smem_u32(slab);
+        const uint32_t pix_bytes = (uint32_t)a.C * 4;
+        {
+            const int cpp = a.C >> 2;                            // 16-byte chunks per pixel
+            const int64_t g0 = q0 + img0 * KH1;                  // first input row (global index) of the slab
+            const int64_t img1 = (q0 + nq - 1) / a.OH;
+            const int rows = nq + KH1 * (int)(img1 - img0 + 1);
+            const int64_t first = g0 * a.W * a.C;                // element offset of the slab in `in`
+            const float *src0 = a.in + first;
+            const int64_t avail = (a.in_elems - first) >> 2;     // chunks that exist past `first`
+            const int total = rows * a.W * cpp;
+            int p = ptid / cpp, j = ptid - p * cpp;              // chunk ptid, then += PRODUCERS per iteration
+            const int dp = Cfg::PRODUCERS / cpp, dj = Cfg::PRODUCERS - dp * cpp;
+            for (int q = ptid; q < total; q += Cfg::PRODUCERS) {
+                const uint32_t dst = slab_u32 + (uint32_t)p * pix_bytes + (uint32_t)(((j & ~7) | ((j ^ p) & 7)) << 4);
+                const bool ok = q < avail;
+                cp_async16_u32(dst, src0 + (ok ? (size_t)q * 4 : 0), ok ? 16 : 0);
+                p += dp; j += dj;
+                if (j >= cpp) { j -= cpp; ++p; }
+            }
+            cp_async_commit();
+            cp_async_wait<0>();
+            asm volatile("bar.sync 1, %0;" ::"n"(Cfg::PRODUCERS) : "memory");
+        }
+        if (prof) t_fill = clock64() - t_start;
+        const long long t_l0 = prof ? clock64() : 0;
+        // ============================ A producers ============================
+        const int r = quad * 32 + lane;                          // GEMM row = TMEM lane
+        int pix0 = 0;
+        if (r < valid) {
+            const int dq = r / a.OW, ow = r - dq * a.OW;
+            pix0 = (dq + KH1 * (int)((q0 + dq) / a.OH - img0)) * a.W + ow;
+        }
+        int is_c0 = 0, is_ss = 0, is_poff = 0;                   // tap state of the next k-block to load
+        const uint32_t lane_addr = ((uint32_t)(quad * 32)) << 16;
+        uint32_t hi[32], lo[32];
+        auto advance = [&]() {
+            is_c0 += TBK;
+            if (is_c0 == a.C) {
+                is_c0 = 0; ++is_poff;
+                if (++is_ss == a.KW) { is_ss = 0; is_poff += a.W - a.KW; }
+            }
+        };
+        for (int q = 0; q < pset; ++q) advance();
+        auto load_split = [&]() {
+            const int p = pix0 + is_poff;
+            const unsigned char *base = slab + (size_t)p * pix_bytes + is_c0 * 4;
+            const uint32_t x = (uint32_t)(p & 7) << 4;
+            uint32_t v[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint4 q = *reinterpret_cast<const uint4 *>(base + (((uint32_t)j << 4) ^ x));
+                v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+            }
+#pragma unroll
+            for (int q = 0; q < NSETS; ++q) advance();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                hi[j] = v[j] & 0xFFFFE000u;
+                lo[j] = __float_as_uint(__uint_as_float(v[j]) - __uint_as_float(hi[j]));
+            }
+        };
+        if (pset < nkb) load_split();
+        for (int kb = pset; kb < nkb; kb += NSETS) {
+            const int st = kb % ST;
+            const long long tw = prof ? clock64() : 0;
+            if (lane == 0) mbar_wait(&emptyA[st], ((kb / ST) & 1) ^ 1, 1);   // one poller / one arrival per warp
+            __syncwarp();
+            if (prof) t_wait += clock64() - tw;
+            tc_fence_after();
+            const uint32_t ta = tmem_base + lane_addr + Cfg::ACC_COLS + st * 2 * TBK;
+            if (!(a.debug_same_addr & 4)) {                       // (timing experiment 4: producers only hand-shake)
+                tmem_st32(ta, hi);
+                tmem_st32(ta + TBK, lo);
+                if (kb + NSETS < nkb) load_split();              // overlaps the TMEM store latency
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&fullA[st]);
+        }
+
+        // ============================ epilogue ============================
+        if (prof) t_loop = clock64() - t_l0;
+        const long long ta0 = prof ? clock64() : 0;
+        if (lane == 0) mbar_wait(accum, 0, 5);                   // all MMAs done => every warp is done with the slab
+        __syncwarp();
+        if (prof) t_acc = clock64() - ta0;
+        tc_fence_after();
+        unsigned char *stage_buf = slab + (pset * 4 + quad) * 4096;           // the slab is idle now: per-warp transpose buffer
+        const int sub = lane >> 3, chunk = lane & 7;
+        const bool has_bias = a.flags & ISS_F_BIAS, pre = a.flags & ISS_F_AFFINE_PRE, post = a.flags & ISS_F_AFFINE_POST;
+        const bool relu = a.flags & ISS_F_RELU, resid = a.flags & ISS_F_RESIDUAL;
+#pragma unroll 1
+        for (int c = pset * 32; c < BN; c += 32 * NSETS) {       // the sets share the columns
+            uint32_t acc[32];
+            {
+                uint32_t corr[32];
+                tmem_ld32(tmem_base + lane_addr + c, acc);
+                tmem_ld32(tmem_base + lane_addr + BN + c, corr);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(corr[j]));
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<uint4 *>(stage_buf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                    make_uint4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+            __syncwarp();
+            const int nb = n0 + c + chunk * 4;
+            float eb[4], es1[4], et1[4], es2[4], et2[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                eb[q] = has_bias ? __ldg(a.bias + nb + q) : 0.f;
+                es1[q] = pre ? __ldg(a.pre_scale + nb + q) : 1.f;  et1[q] = pre ? __ldg(a.pre_shift + nb + q) : 0.f;
+                es2[q] = post ? __ldg(a.post_scale + nb + q) : 1.f; et2[q] = post ? __ldg(a.post_shift + nb + q) : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int rl = 4 * i + sub;
+                const int rr = quad * 32 + rl;
+                const int64_t m = mbase + rr;
+                const uint4 q4 = *reinterpret_cast<const uint4 *>(stage_buf + rl * 128 + ((chunk ^ (rl & 7)) << 4));
+                if (rr < valid) {
+                    float y[4] = {__uint_as_float(q4.x), __uint_as_float(q4.y), __uint_as_float(q4.z), __uint_as_float(q4.w)};
+                    float4 rs = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (resid) rs = __ldg(reinterpret_cast<const float4 *>(a.residual + m * a.N + nb));
+                    const float rv[4] = {rs.x, rs.y, rs.z, rs.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float t = y[q] + eb[q];
+                        if (pre) t = fmaf(t, es1[q], et1[q]);
+                        if (resid) t += rv[q];
+                        if (relu) t = fmaxf(t, 0.f);
+                        if (post) t = fmaf(t, es2[q], et2[q]);
+                        y[q] = t;
+                    }
+                    *reinterpret_cast<float4 *>(a.out + m * a.N + nb) = make_float4(y[0], y[1], y[2], y[3]);
+                }
+            }
+        }
+        if (prof) {
+            atomicAdd(a.prof + 4, (unsigned long long)t_loop); atomicAdd(a.prof + 5, (unsigned long long)t_wait);
+            atomicAdd(a.prof + 7, (unsigned long long)t_fill); atomicAdd(a.prof + 9, (unsigned long long)t_acc);
+            atomicAdd(a.prof + 8, (unsigned long long)(clock64() - ta0 - t_acc)); atomicAdd(a.prof + 10, 1ull);
+            atomicAdd(a.prof + 11, (unsigned long long)(clock64() - t_start));
+        }
+        tc_fence_before();
+    } else {
+        // ============================ B loader + MMA issuer (warp 4) ============================
+        tc_issuer_warp<BN, SB, ST, Cfg::B_STAGE, Cfg::ACC_COLS>(a, tmem_base, b_ring, fullA, emptyA, fullB, emptyB, accum, nkb);
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
+    }
+}
+
+constexpr int SMEM_CTA_MAX = 232448;       // 227 KB opt-in limit per CTA
+constexpr int SMEM_HALF_SM = 115712;       // two CTAs per SM: 2 * (x + 1 KB reserved) <= 228 KB
+
+template <int BN, int SB, int ST, int NSETS = 1>
+int launch_tc3(const ConvArgs &a, int slab_bytes, cudaStream_t st)
+{
+    using Cfg = Tc3Cfg<BN, SB, ST, NSETS>;
+    auto kern = conv_gemm_tc3_kernel<BN, SB, ST, NSETS>;
+    static bool configured = false;
+    if (!configured) {
+        ISS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CTA_MAX));
+        configured = true;
+    }
+    const int64_t Q = a.M / a.OW;
+    const int64_t gm = (Q + a.slab_R - 1) / a.slab_R;
+    ISS_REQUIRE(gm < (1ll << 31), ISS_ERR_INVALID, "conv_tc: M too large");
+    dim3 grid((unsigned)gm, (unsigned)(a.N / BN));
+    kern<<<grid, Cfg::THREADS, Cfg::FIXED + slab_bytes, st>>>(a);
+    ISS_CUDA_OK(cudaGetLastError());
+    iss_count_launch();
+    return ISS_OK;
+}
+
+unsigned long long *g_prof = nullptr;
+void prof_dump()
+{
+    unsigned long long h[12];
+    if (!g_prof || cudaMemcpy(h, g_prof, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess || !h[10]) return;
+    const double n = (double)h[10];
+    fprintf(stderr, "libiss_b200 tc3 prof (cycles per CTA, %.0f CTAs): issuer loop %.0f = wait fullB %.0f + wait fullA %.0f + wait emptyB %.0f + issue; "
+            "producer: fill %.0f, loop %.0f (wait emptyA %.0f), accum wait %.0f, epilogue %.0f, total %.0f\n",
+            n, h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[7] / n, h[4] / n, h[5] / n, h[9] / n, h[8] / n, h[11] / n);
+}
+
+// Slab kernel dispatch; returns 1 if the layer is not eligible (caller falls back to tc2).
+int try_launch_slab(ConvArgs &a, cudaStream_t st)
+{
+    static const int want_prof = [] { const char *e = getenv("ISS_B200_TC_PROF"); return e ? atoi(e) : 0; }();
+    if (want_prof && !g_prof) {
+        if (cudaMalloc(&g_prof, 12 * sizeof(unsigned long long)) == cudaSuccess) { cudaMemset(g_prof, 0, 12 * sizeof(unsigned long long)); atexit(prof_dump); }
+    }
+    a.prof = (want_prof && a.N == want_prof) ? g_prof : nullptr;      // ISS_B200_TC_PROF=<N of the layers to instrument>
+    if (a.SH != 1 || a.SW != 1 || a.PT != 0 || a.PL != 0 || a.KH * a.KW <= 1) return 1;
+    if (a.OH != a.H - a.KH + 1 || a.OW != a.W - a.KW + 1 || a.OW > TBM || a.Kp != a.K || a.N % 64 != 0) return 1;
+    const int R = TBM / a.OW;
+    const int cross = (R - 1) / a.OH + 1;                        // image boundaries a tile can contain
+    const int rows = R + (a.KH - 1) * (1 + cross);
+    int slab_bytes = rows * a.W * a.C * 4;
+    if (slab_bytes < 32768) slab_bytes = 32768;                  // doubles as the 8 x 4 KB epilogue transpose buffers
+    a.slab_R = R;
+    a.slab_rows = rows;
+    a.in_elems = a.M / ((int64_t)a.OH * a.OW) * a.H * a.W * a.C;
+    static const int cfg = [] { const char *e = getenv("ISS_B200_TC3_CFG"); return e ? atoi(e) : 0; }();   // experiments
+    if (cfg == 1 && a.N % 128 != 0 && Tc3Cfg<64, 4, 6>::FIXED + slab_bytes <= SMEM_CTA_MAX) return launch_tc3<64, 4, 6, 1>(a, slab_bytes, st);
+    if (cfg == 2 && a.N % 128 != 0 && Tc3Cfg<64, 4, 6>::FIXED + slab_bytes <= SMEM_CTA_MAX) return launch_tc3<64, 4, 6, 2>(a, slab_bytes, st);
+    if (cfg == 2 && a.N % 128 == 0 && Tc3Cfg<128, 3, 4>::FIXED + slab_bytes <= SMEM_CTA_MAX) return launch_tc3<128, 3, 4, 2>(a, slab_bytes, st);
+    if (a.N % 128 == 0) {
+        if (Tc3Cfg<128, 4, 4>::FIXED + slab_bytes <= SMEM_CTA_MAX) return launch_tc3<128, 4, 4>(a, slab_bytes, st);
+        if (Tc3Cfg<128, 3, 4>::FIXED + slab_bytes <= SMEM_CTA_MAX) return launch_tc3<128, 3, 4>(a, slab_bytes, st);
+        if (Tc3Cfg<128, 2, 4>::FIXED + slab_bytes <= SMEM_CTA_MAX) return launch_tc3<128, 2, 4>(a, slab_bytes, st);
+        return 1;
+    }
+    if (Tc3Cfg<64, 3, 2>::FIXED + slab_bytes <= SMEM_HALF_SM) return launch_tc3<64, 3, 2>(a, slab_bytes, st);
+    if (Tc3Cfg<64, 2, 2>::FIXED + slab_bytes <= SMEM_HALF_SM) return launch_tc3<64, 2, 2>(a, slab_bytes, st);
+    if (Tc3Cfg<64, 3, 2>::FIXED + slab_bytes <= SMEM_CTA_MAX) return launch_tc3<64, 3, 2>(a, slab_bytes, st);
+    return 1;
 }
 
 template <int BN, int DA, int SB, int ST, int NSETS = 1>
@@ -747,6 +1095,11 @@ int iss_launch_conv_tc(const ConvArgs &a_in, int mode, cudaStream_t st)
         if (two_sets) {
             if (a.N % 128 == 0) return launch_tc2<128, 2, 4, 4, 2>(a, st);   // 193 KB smem, 512 TMEM cols
             if (a.N % 64 == 0) return launch_tc2<64, 2, 4, 6, 2>(a, st);     // 129 KB smem (=> ~96 KB L1), 512 TMEM cols
+        }
+        static const int slab = [] { const char *e = getenv("ISS_B200_TC_SLAB"); return (e && e[0] == '0') ? 0 : 1; }();
+        if (slab) {                                                      // un-padded stride-1 KHxKW convs: input slab in smem
+            const int rc = try_launch_slab(a, st);
+            if (rc != 1) return rc;
         }
         if (a.N % 128 == 0) return launch_tc2<128, 4, 4, 4>(a, st);      // 193 KB smem, 512 TMEM cols (2x128 acc + 4 A stages), 1 CTA/SM
         if (a.N % 64 == 0) return launch_tc2<64, 3, 3, 2>(a, st);        //  97 KB smem, 256 TMEM cols, 2 CTAs/SM
