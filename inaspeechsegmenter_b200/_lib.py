@@ -36,6 +36,7 @@ F_BIAS, F_AFFINE_PRE, F_RELU, F_AFFINE_POST, F_SOFTMAX, F_SIGMOID = 1, 2, 4, 8, 
 PCM_F32, PCM_S16 = 0, 1
 FFT_FP32, FFT_FP64 = 0, 1
 GEMM_FP32, GEMM_TC_SS, GEMM_TC_TS = 0, 1, 2
+GEMM_TC_F16_EXPERIMENTAL = 3          # csrc/conv_gemm_tc_f16.cu: not validated on hardware yet
 
 # name -> (restype, argtypes); must list every symbol include/iss_b200.h declares
 _vp, _i, _i64, _d = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_double

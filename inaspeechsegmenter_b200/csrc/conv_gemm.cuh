@@ -33,6 +33,7 @@ struct ConvArgs {
 #define ISS_GEMM_FP32  0      /* fp32 CUDA cores (conv_gemm.cu) */
 #define ISS_GEMM_TC_SS 1      /* tcgen05 3xTF32, A and B from shared memory */
 #define ISS_GEMM_TC_TS 2      /* tcgen05 3xTF32, A from tensor memory, B from shared memory */
+#define ISS_GEMM_TC_F16 3     /* EXPERIMENTAL (not yet run on hardware): fp16 hi/lo split, kind::f16, conv_gemm_tc_f16.cu; other layers as engine 2 */
 #ifndef ISS_GEMM_DEFAULT
 #define ISS_GEMM_DEFAULT ISS_GEMM_TC_TS
 #endif

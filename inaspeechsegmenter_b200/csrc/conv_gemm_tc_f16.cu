@@ -1,0 +1,393 @@
+// conv_gemm_tc_f16.cu -- EXPERIMENTAL engine 3 (ISS_B200_GEMM=tc_f16, never the default): the slab
+// convolution of conv_gemm_tc.cu with the operands split into TWO fp16 numbers instead of two TF32 ones.
+//
+//      x = hi + lo,  hi = fp16(x),  lo = fp16(x - hi)          (22 significant bits, like the TF32 split)
+//      A.B ~= Ah.Bh + Ah.Bl + Al.Bh                            (three kind::f16 MMAs, fp32 accumulation)
+//
+// kind::f16 runs at twice the kind::tf32 rate and its operands are half as wide, so one 128-byte swizzle
+// row holds 64 k-elements: per unit of K the tensor time, the weight-tile bytes, the TMEM-store bytes and --
+// what bounds the TF32 kernel today -- the number of producer/issuer hand-shakes all halve.
+// The weights of a layer are pre-scaled by an exact power of two so that max|w| lands in [2^12, 2^13) (fp16
+// keeps 11 bits down to 6e-5 and is exact to 6e-8 below; the scale is undone in the epilogue); activations
+// are used as they are, so |activation| must stay below 65504 (true after BatchNorm/z-normalisation; a
+// network that violates it produces inf and must use engine 2).
+// Algorithmic accuracy of the split (exact products and sums, tests/test_split_accuracy.py): 8e-7 on the
+// stand-in VAD softmax vs 1.3e-6 for the TF32 split -- both at the fp32 oracle's own rounding noise.
+//
+// STATUS: written in round 1 after the GPU budget was spent -- compiles for sm_100a, NOT yet run on hardware.
+// Open points to verify first in round 2 (tools/tc_check.py 3): the packing of 16-bit A operands in tensor
+// memory (assumed: 32-bit column c of lane m holds k = 2c in its low half, k = 2c+1 in its high half).
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <math.h>
+#include <stdlib.h>
+
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "tc_common.cuh"
+
+int iss_launch_conv_tc_f16(ConvArgs &a, cudaStream_t st);
+
+namespace {
+
+constexpr int HBK = 64;                     // k-elements per block = one 128-byte swizzle row of halves
+
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+template <int BN, int SB, int ST>
+struct TcHCfg {
+    static constexpr int THREADS = 160;
+    static constexpr int B_TILE = BN * 128;                              // BN rows x 64 halves
+    static constexpr int B_STAGE = 2 * B_TILE;                           // hi | lo
+    static constexpr uint32_t ACC_COLS = 2 * BN;                         // D_main | D_lo
+    static constexpr uint32_t A_COLS = 64;                               // 32 packed columns hi + 32 lo per stage
+    static constexpr uint32_t TMEM_COLS = tmem_cols_pow2(ACC_COLS + ST * A_COLS);
+    static constexpr int FIXED = SB * B_STAGE + 1024 + 256;              // + slab bytes
+};
+
+struct F16Args {
+    const unsigned char *wt;    // tiled fp16 image [n-tile][k-block][hi|lo][BN rows x 128 B, SWIZZLE_128B]
+    float inv_scale;
+};
+
+template <int BN, int SB, int ST>
+__global__ void __launch_bounds__(160, (TcHCfg<BN, SB, ST>::TMEM_COLS <= 256 ? 2 : 1))
+conv_gemm_tc3h_kernel(const ConvArgs a, const F16Args h)
+{
+    using Cfg = TcHCfg<BN, SB, ST>;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    unsigned char *b_ring = smem;
+    unsigned char *slab = smem + SB * Cfg::B_STAGE;
+    const int slab_bytes = a.slab_rows * a.W * a.C * 4 < 32768 ? 32768 : a.slab_rows * a.W * a.C * 4;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(slab + slab_bytes);
+    uint64_t *fullA = bars, *emptyA = bars + ST, *emptyB = bars + 2 * ST, *fullB = bars + 2 * ST + SB, *accum = bars + 2 * ST + 2 * SB;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * ST + 2 * SB + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n0 = blockIdx.y * BN;
+    const int nkb = a.K / HBK;
+    const int R = a.slab_R, KH1 = a.KH - 1;
+    const int64_t Q = a.M / a.OW;
+    const int64_t q0 = (int64_t)blockIdx.x * R;
+    const int64_t mbase = q0 * a.OW;
+    const int nq = (int)((Q - q0) < (int64_t)R ? (Q - q0) : (int64_t)R);
+    const int valid = nq * a.OW;
+    const int64_t img0 = q0 / a.OH;
+
+    if (tid == 0) {
+        for (int s = 0; s < ST; ++s) { mbar_init(&fullA[s], 4); mbar_init(&emptyA[s], 1); }
+        for (int s = 0; s < SB; ++s) { mbar_init(&emptyB[s], 1); mbar_init(&fullB[s], 1); }
+        mbar_init(accum, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp != 4) {
+        // ============================ slab fill (as conv_gemm_tc3_kernel) ============================
+        const int quad = warp;
+        const uint32_t slab_u32 = smem_u32(slab);
+        const uint32_t pix_bytes = (uint32_t)a.C * 4;
+        {
+            const int cpp = a.C >> 2;
+            const int64_t g0 = q0 + img0 * KH1;
+            const int64_t img1 = (q0 + nq - 1) / a.OH;
+            const int rows = nq + KH1 * (int)(img1 - img0 + 1);
+            const int64_t first = g0 * a.W * a.C;
+            const float *src0 = a.in + first;
+            const int64_t avail = (a.in_elems - first) >> 2;
+            const int total = rows * a.W * cpp;
+            int p = tid / cpp, j = tid - p * cpp;
+            const int dp = 128 / cpp, dj = 128 - dp * cpp;
+            for (int q = tid; q < total; q += 128) {
+                const uint32_t dst = slab_u32 + (uint32_t)p * pix_bytes + (uint32_t)(((j & ~7) | ((j ^ p) & 7)) << 4);
+                const bool ok = q < avail;
+                cp_async16_u32(dst, src0 + (ok ? (size_t)q * 4 : 0), ok ? 16 : 0);
+                p += dp; j += dj;
+                if (j >= cpp) { j -= cpp; ++p; }
+            }
+            cp_async_commit();
+            cp_async_wait<0>();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        // ============================ A producers ============================
+        const int r = quad * 32 + lane;
+        int pix0 = 0;
+        if (r < valid) {
+            const int dq = r / a.OW, ow = r - dq * a.OW;
+            pix0 = (dq + KH1 * (int)((q0 + dq) / a.OH - img0)) * a.W + ow;
+        }
+        int is_c0 = 0, is_ss = 0, is_poff = 0;
+        const uint32_t lane_addr = ((uint32_t)(quad * 32)) << 16;
+        uint32_t hi[32], lo[32];                                 // 64 k-elements, two halves per register
+        auto load_split = [&]() {
+            const int p = pix0 + is_poff;
+            const unsigned char *base = slab + (size_t)p * pix_bytes + is_c0 * 4;
+            const uint32_t x = (uint32_t)(p & 7) << 4;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {               // 2 x 32 floats keeps the register peak down
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 q = *reinterpret_cast<const float4 *>(base + ((((uint32_t)(half * 8 + j)) << 4) ^ x));
+                    v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);      // low half = even k
+                    const float2 hf = __half22float2(hh);
+                    const __half2 ll = __floats2half2_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+                    hi[half * 16 + i] = *reinterpret_cast<const uint32_t *>(&hh);
+                    lo[half * 16 + i] = *reinterpret_cast<const uint32_t *>(&ll);
+                }
+            }
+            is_c0 += HBK;
+            if (is_c0 == a.C) {
+                is_c0 = 0; ++is_poff;
+                if (++is_ss == a.KW) { is_ss = 0; is_poff += a.W - a.KW; }
+            }
+        };
+        load_split();
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int st = kb % ST;
+            if (lane == 0) mbar_wait(&emptyA[st], ((kb / ST) & 1) ^ 1, 1);
+            __syncwarp();
+            tc_fence_after();
+            const uint32_t ta = tmem_base + lane_addr + Cfg::ACC_COLS + st * Cfg::A_COLS;
+            tmem_st32(ta, hi);
+            tmem_st32(ta + 32, lo);
+            if (kb + 1 < nkb) load_split();
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&fullA[st]);
+        }
+
+        // ============================ epilogue ============================
+        if (lane == 0) mbar_wait(accum, 0, 5);
+        __syncwarp();
+        tc_fence_after();
+        unsigned char *stage_buf = slab + quad * 4096;
+        const int sub = lane >> 3, chunk = lane & 7;
+        const bool has_bias = a.flags & ISS_F_BIAS, pre = a.flags & ISS_F_AFFINE_PRE, post = a.flags & ISS_F_AFFINE_POST;
+        const bool relu = a.flags & ISS_F_RELU, resid = a.flags & ISS_F_RESIDUAL;
+        const float inv_s = h.inv_scale;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            uint32_t acc[32];
+            {
+                uint32_t corr[32];
+                tmem_ld32(tmem_base + lane_addr + c, acc);
+                tmem_ld32(tmem_base + lane_addr + BN + c, corr);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint((__uint_as_float(acc[j]) + __uint_as_float(corr[j])) * inv_s);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<uint4 *>(stage_buf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                    make_uint4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+            __syncwarp();
+            const int nb = n0 + c + chunk * 4;
+            float eb[4], es1[4], et1[4], es2[4], et2[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                eb[q] = has_bias ? __ldg(a.bias + nb + q) : 0.f;
+                es1[q] = pre ? __ldg(a.pre_scale + nb + q) : 1.f;  et1[q] = pre ? __ldg(a.pre_shift + nb + q) : 0.f;
+                es2[q] = post ? __ldg(a.post_scale + nb + q) : 1.f; et2[q] = post ? __ldg(a.post_shift + nb + q) : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int rl = 4 * i + sub;
+                const int rr = quad * 32 + rl;
+                const int64_t m = mbase + rr;
+                const uint4 q4 = *reinterpret_cast<const uint4 *>(stage_buf + rl * 128 + ((chunk ^ (rl & 7)) << 4));
+                if (rr < valid) {
+                    float y[4] = {__uint_as_float(q4.x), __uint_as_float(q4.y), __uint_as_float(q4.z), __uint_as_float(q4.w)};
+                    float4 rs = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (resid) rs = __ldg(reinterpret_cast<const float4 *>(a.residual + m * a.N + nb));
+                    const float rv[4] = {rs.x, rs.y, rs.z, rs.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float t = y[q] + eb[q];
+                        if (pre) t = fmaf(t, es1[q], et1[q]);
+                        if (resid) t += rv[q];
+                        if (relu) t = fmaxf(t, 0.f);
+                        if (post) t = fmaf(t, es2[q], et2[q]);
+                        y[q] = t;
+                    }
+                    *reinterpret_cast<float4 *>(a.out + m * a.N + nb) = make_float4(y[0], y[1], y[2], y[3]);
+                }
+            }
+        }
+        tc_fence_before();
+    } else {
+        // ============================ B loader + MMA issuer (warp 4, warp-uniform; see tc_issuer_warp) ============================
+        // instruction descriptor: D = F32 (bits 4-5 = 1), A = B = F16 (bits 7-9, 10-12 = 0), both K-major, N >> 3, M >> 4
+        constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+        constexpr uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+        const uint32_t tb = __reduce_or_sync(0xffffffffu, tmem_base);
+        const unsigned char *wt = h.wt + (size_t)blockIdx.y * nkb * Cfg::B_STAGE;
+        auto issue_b = [&](int kb) {
+            if (kb < nkb) {
+                const int sl = kb % SB;
+                if (elect_one()) {
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&fullB[sl])), "r"((uint32_t)Cfg::B_STAGE) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(smem_u32(b_ring + sl * Cfg::B_STAGE)), "l"(wt + (size_t)kb * Cfg::B_STAGE),
+                                   "r"((uint32_t)Cfg::B_STAGE), "r"(smem_u32(&fullB[sl])) : "memory");
+                }
+                __syncwarp();
+            }
+        };
+        for (int p = 0; p < SB - 1; ++p) issue_b(p);
+        const uint32_t d_main = tb, d_lo = tb + BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int st = kb % ST, sl = kb % SB;
+            mbar_wait(&fullB[sl], (kb / SB) & 1, 2);
+            mbar_wait(&fullA[st], (kb / ST) & 1, 3);
+            tc_fence_after();
+            const uint64_t dbh = make_sw128_desc(smem_u32(b_ring + sl * Cfg::B_STAGE));
+            const uint32_t ta = tb + Cfg::ACC_COLS + st * Cfg::A_COLS;
+            if (elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < HBK / 16; ++kk) {          // K = 16 per kind::f16 MMA = 8 packed TMEM columns = 32 smem bytes
+                    const uint32_t first = (kb > 0 || kk > 0) ? 1u : 0u;
+                    umma_f16_ts(d_main, ta + kk * 8, dbh + 2 * kk, idesc2, first);           // Ah.[Bh | Bl]
+                    umma_f16_ts(d_lo, ta + 32 + kk * 8, dbh + 2 * kk, idesc, 1u);            // Al.Bh
+                }
+                umma_commit(&emptyA[st]);
+                umma_commit(&emptyB[sl]);
+                if (kb == nkb - 1) umma_commit(accum);
+            }
+            __syncwarp();
+            if (kb + SB - 1 < nkb) {
+                if (kb >= 1) mbar_wait(&emptyB[(kb - 1) % SB], ((kb - 1) / SB) & 1, 4);
+                issue_b(kb + SB - 1);
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
+    }
+}
+
+constexpr int SMEM_CTA_MAX = 232448;
+constexpr int SMEM_HALF_SM = 115712;
+
+template <int BN, int SB, int ST>
+int launch_tc3h(const ConvArgs &a, const F16Args &h, int slab_bytes, cudaStream_t st)
+{
+    using Cfg = TcHCfg<BN, SB, ST>;
+    auto kern = conv_gemm_tc3h_kernel<BN, SB, ST>;
+    static bool configured = false;
+    if (!configured) {
+        ISS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CTA_MAX));
+        configured = true;
+    }
+    const int64_t Q = a.M / a.OW;
+    const int64_t gm = (Q + a.slab_R - 1) / a.slab_R;
+    ISS_REQUIRE(gm < (1ll << 31), ISS_ERR_INVALID, "conv_tc_f16: M too large");
+    dim3 grid((unsigned)gm, (unsigned)(a.N / BN));
+    kern<<<grid, Cfg::THREADS, Cfg::FIXED + slab_bytes, st>>>(a, h);
+    ISS_CUDA_OK(cudaGetLastError());
+    iss_count_launch();
+    return ISS_OK;
+}
+
+// fp16 weight images, built on first use from the fp32 planes the layer already holds on the device
+// (wt_hi + wt_lo == the original weight, exactly) and cached by their address.
+struct F16Image { unsigned char *d; float inv_scale; };
+std::map<const float *, F16Image> g_images;
+std::mutex g_images_mu;
+
+int get_image(const ConvArgs &a, int BN, F16Image *out)
+{
+    std::lock_guard<std::mutex> lk(g_images_mu);
+    auto it = g_images.find(a.wt_tiled);
+    if (it != g_images.end()) { *out = it->second; return ISS_OK; }
+    const size_t plane = (size_t)a.N * a.Kp;
+    std::vector<float> hi(plane), lo(plane);
+    ISS_CUDA_OK(cudaMemcpy(hi.data(), a.wt_hi, plane * sizeof(float), cudaMemcpyDeviceToHost));
+    ISS_CUDA_OK(cudaMemcpy(lo.data(), a.wt_lo, plane * sizeof(float), cudaMemcpyDeviceToHost));
+    float maxabs = 0.f;
+    for (size_t i = 0; i < plane; ++i) { hi[i] += lo[i]; maxabs = fmaxf(maxabs, fabsf(hi[i])); }
+    int e = 0;
+    if (maxabs > 0.f) frexpf(maxabs, &e);                       // maxabs in [2^(e-1), 2^e)
+    const float scale = ldexpf(1.f, 13 - e);                    // scaled max in [2^12, 2^13)
+    const int nkb = a.K / HBK;
+    std::vector<__half> img((size_t)2 * a.N * a.K);
+    for (int nt = 0; nt < a.N / BN; ++nt)
+        for (int kb = 0; kb < nkb; ++kb)
+            for (int n = 0; n < BN; ++n)
+                for (int k = 0; k < HBK; ++k) {
+                    const float w = hi[(size_t)(nt * BN + n) * a.Kp + kb * HBK + k] * scale;
+                    const __half h = __float2half_rn(w);
+                    const __half l = __float2half_rn(w - __half2float(h));
+                    const int chunk = (k >> 3) ^ (n & 7);            // 16-byte chunk = 8 halves
+                    const size_t base = (((size_t)nt * nkb + kb) * 2) * (size_t)BN * HBK;
+                    img[base + (size_t)n * HBK + chunk * 8 + (k & 7)] = h;
+                    img[base + (size_t)BN * HBK + (size_t)n * HBK + chunk * 8 + (k & 7)] = l;
+                }
+    F16Image im;
+    im.inv_scale = 1.f / scale;
+    ISS_CUDA_OK(cudaMalloc(&im.d, img.size() * sizeof(__half)));
+    ISS_CUDA_OK(cudaMemcpy(im.d, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    g_images[a.wt_tiled] = im;
+    *out = im;
+    return ISS_OK;
+}
+
+}  // namespace
+
+// Returns 1 when the layer is not covered (caller continues with the TF32 engines).
+int iss_launch_conv_tc_f16(ConvArgs &a, cudaStream_t st)
+{
+    if (a.SH != 1 || a.SW != 1 || a.PT != 0 || a.PL != 0 || a.KH * a.KW <= 1) return 1;
+    if (a.OH != a.H - a.KH + 1 || a.OW != a.W - a.KW + 1 || a.OW > TBM || a.Kp != a.K) return 1;
+    if (a.N % 64 != 0 || a.C % HBK != 0 || a.K % HBK != 0) return 1;
+    const int R = TBM / a.OW;
+    const int cross = (R - 1) / a.OH + 1;
+    const int rows = R + (a.KH - 1) * (1 + cross);
+    int slab_bytes = rows * a.W * a.C * 4;
+    if (slab_bytes < 32768) slab_bytes = 32768;
+    a.slab_R = R;
+    a.slab_rows = rows;
+    a.in_elems = a.M / ((int64_t)a.OH * a.OW) * a.H * a.W * a.C;
+    a.prof = nullptr;
+    const int BN = a.N % 128 == 0 ? 128 : 64;                   // same n-tiling as iss_prepare_tc_weights
+    F16Image im;
+    const int rc = get_image(a, BN, &im);
+    if (rc != ISS_OK) return rc;
+    F16Args h{im.d, im.inv_scale};
+    if (BN == 128) {
+        if (TcHCfg<128, 4, 4>::FIXED + slab_bytes <= SMEM_CTA_MAX) return launch_tc3h<128, 4, 4>(a, h, slab_bytes, st);
+        if (TcHCfg<128, 3, 4>::FIXED + slab_bytes <= SMEM_CTA_MAX) return launch_tc3h<128, 3, 4>(a, h, slab_bytes, st);
+        if (TcHCfg<128, 2, 4>::FIXED + slab_bytes <= SMEM_CTA_MAX) return launch_tc3h<128, 2, 4>(a, h, slab_bytes, st);
+        return 1;
+    }
+    if (TcHCfg<64, 3, 2>::FIXED + slab_bytes <= SMEM_HALF_SM) return launch_tc3h<64, 3, 2>(a, h, slab_bytes, st);
+    if (TcHCfg<64, 2, 2>::FIXED + slab_bytes <= SMEM_HALF_SM) return launch_tc3h<64, 2, 2>(a, h, slab_bytes, st);
+    if (TcHCfg<64, 3, 2>::FIXED + slab_bytes <= SMEM_CTA_MAX) return launch_tc3h<64, 3, 2>(a, h, slab_bytes, st);
+    return 1;
+}

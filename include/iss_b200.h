@@ -51,9 +51,11 @@ int iss_ctx_destroy(iss_ctx *ctx);
 int64_t iss_launch_count(void);
 /* GEMM engine used by the conv / dense layers of K2 and K5 (process-wide):
  * 0 = fp32 CUDA cores, 1 = tcgen05 3xTF32 with both operands in shared memory,
- * 2 = tcgen05 3xTF32 with the activation operand in tensor memory.  All three
- * are sm_100a code paths of this library with fp32-class accuracy; the default
- * can be overridden with the environment variable ISS_B200_GEMM=fp32|tc_ss|tc_ts. */
+ * 2 = tcgen05 3xTF32 with the activation operand in tensor memory (default).  All
+ * three are sm_100a code paths of this library with fp32-class accuracy; the default
+ * can be overridden with the environment variable ISS_B200_GEMM=fp32|tc_ss|tc_ts.
+ * 3 (tc_f16) = EXPERIMENTAL fp16 hi/lo-split variant of 2 for un-padded convolutions
+ * (csrc/conv_gemm_tc_f16.cu; not validated on hardware yet, never selected by default). */
 int iss_set_gemm_mode(int mode);
 int iss_get_gemm_mode(void);
 

@@ -7,7 +7,7 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from inaspeechsegmenter_b200 import _lib, engine, vbx_segmenter as vb     # noqa: E402
 from oracle import vbx_oracle as vx                                        # noqa: E402

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """VBx x-vector path (BASELINE configs[3]) on synthetic audio: K4 features + K5 ResNet101, timed with CUDA events.
-   python tools/vbx_profile.py [minutes]"""
+   python tests/tools/vbx_profile.py [minutes]"""
 import os
 import sys
 import time
@@ -8,7 +8,7 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 from conftest import synth_audio                                            # noqa: E402
