@@ -273,7 +273,10 @@ def is_mid_speech(start, stop, speech):
 
 def add_needed_vectors(xvectors, t_mid):
     """Keep at least 50 % of the windows whose midpoint is in speech (:40-52): when the
-    overlap threshold removed too many, the windows are taken back in decreasing overlap order."""
+    overlap threshold removed too many, the windows are taken back in decreasing overlap order.
+    (The reference sorts a ragged object array and reads ``Segment.stop``, which pyannote's Segment
+    does not define; this implements the documented intent with the same selection rule: sort by
+    overlap ratio descending, skip the first len(xvectors) entries, take the next ``diff``.)"""
     min_pred = round(0.5 * len(t_mid))
     if len(xvectors) < min_pred:
         order = np.argsort(np.array([t[0] for t in t_mid], dtype=np.float64))[::-1]
