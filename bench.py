@@ -320,9 +320,13 @@ def run_b200(args):
     peak_tf = peaks.get('bf16_tflops_sustained') or 1400.0
     peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)' if 'bf16_tflops_sustained' in peaks else 'fallback 1.4 PFLOP/s sustained (of fallback)'
     ach = (fl.value / max(nlaunch.value, 1)) / (tms.value / max(nlaunch.value, 1) * 1e-3) / 1e12 if tms.value > 0 else 0.0
-    gemm = {0: 'fp32 CUDA cores', 1: 'tcgen05 3xTF32 (A,B from smem)', 2: 'tcgen05 3xTF32 (A from TMEM)'}[lib.iss_get_gemm_mode()]
+    mode = lib.iss_get_gemm_mode()
+    gemm = {0: 'fp32 CUDA cores', 1: 'tcgen05 3xTF32 (A,B from smem)', 2: 'tcgen05 3xTF32 (A from TMEM)'}.get(mode, 'engine %d' % mode)
+    traffic, traffic_src = None, None
+    if mode == 2 and os.environ.get('ISS_B200_TC_SLAB', '1') != '0' and not os.environ.get('ISS_B200_TC3_CFG'):
+        traffic, traffic_src = ncu_dram_bytes(os.path.join(ROOT, 'profiles', 'r01_conv_gemm_tc3_final_full.txt'), 'conv_gemm_tc3_kernel<64')
     roof = {'bound': 'tensor', 'kernel': 'conv_gemm %s (VAD layer %d: %s)' % (gemm, dom, layer_name(seg.vad.nn.lowered.descs[dom])),
-            'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf, 'traffic': None,
+            'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf, 'traffic': traffic, 'traffic_source': traffic_src,
             'peak_source': peak_src, 'launches': int(nlaunch.value), 'avg_launch_ms': tms.value / max(nlaunch.value, 1),
             'flops_per_launch': fl.value / max(nlaunch.value, 1), 'share_of_step': tms.value / ms}
 
@@ -354,6 +358,26 @@ def run_b200(args):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def ncu_dram_bytes(path, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum (bytes per launch) of `kernel` from a committed
+    `ncu --set full` summary of the same 2048-patch launch; (None, None) if the file is not there."""
+    try:
+        tot, hit = 0.0, False
+        for line in open(path):
+            if line.startswith('kernel:'):
+                if hit:
+                    break
+                hit = kernel in line
+            elif hit and ('dram__bytes_read.sum ' in line or 'dram__bytes_write.sum ' in line):
+                val, unit = line.split()[-2:]
+                tot += float(val) * {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[unit]
+        if hit and tot > 0:
+            return tot, 'ncu --set full, %s (bytes per launch, cold cache)' % os.path.relpath(path, ROOT)
+    except Exception:
+        pass
+    return None, None
 
 
 def layer_name(d):
