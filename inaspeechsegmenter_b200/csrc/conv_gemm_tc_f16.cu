@@ -44,6 +44,15 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
         "}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// Explicit shared-space load: through a generic pointer ptxas emits LD.E.128 with 64-bit address arithmetic for
+// the slab reads (seen in conv_gemm_tc3_kernel's SASS; to be changed there too once this variant is validated).
+__device__ __forceinline__ float4 lds128(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
 template <int BN, int SB, int ST>
 struct TcHCfg {
     static constexpr int THREADS = 160;
@@ -139,14 +148,14 @@ conv_gemm_tc3h_kernel(const ConvArgs a, const F16Args h)
         uint32_t hi[32], lo[32];                                 // 64 k-elements, two halves per register
         auto load_split = [&]() {
             const int p = pix0 + is_poff;
-            const unsigned char *base = slab + (size_t)p * pix_bytes + is_c0 * 4;
+            const uint32_t base = slab_u32 + (uint32_t)p * pix_bytes + (uint32_t)is_c0 * 4;
             const uint32_t x = (uint32_t)(p & 7) << 4;
 #pragma unroll
             for (int half = 0; half < 2; ++half) {               // 2 x 32 floats keeps the register peak down
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float4 q = *reinterpret_cast<const float4 *>(base + ((((uint32_t)(half * 8 + j)) << 4) ^ x));
+                    const float4 q = lds128(base + ((((uint32_t)(half * 8 + j)) << 4) ^ x));
                     v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
                 }
 #pragma unroll
