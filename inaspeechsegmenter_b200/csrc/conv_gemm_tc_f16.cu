@@ -26,6 +26,7 @@
 #include <mutex>
 #include <vector>
 
+#include "f16_image.cuh"
 #include "tc_common.cuh"
 
 int iss_launch_conv_tc_f16(ConvArgs &a, cudaStream_t st);
@@ -339,25 +340,9 @@ int get_image(const ConvArgs &a, int BN, F16Image *out)
     std::vector<float> hi(plane), lo(plane);
     ISS_CUDA_OK(cudaMemcpy(hi.data(), a.wt_hi, plane * sizeof(float), cudaMemcpyDeviceToHost));
     ISS_CUDA_OK(cudaMemcpy(lo.data(), a.wt_lo, plane * sizeof(float), cudaMemcpyDeviceToHost));
-    float maxabs = 0.f;
-    for (size_t i = 0; i < plane; ++i) { hi[i] += lo[i]; maxabs = fmaxf(maxabs, fabsf(hi[i])); }
-    int e = 0;
-    if (maxabs > 0.f) frexpf(maxabs, &e);                       // maxabs in [2^(e-1), 2^e)
-    const float scale = ldexpf(1.f, 13 - e);                    // scaled max in [2^12, 2^13)
-    const int nkb = a.K / HBK;
-    std::vector<__half> img((size_t)2 * a.N * a.K);
-    for (int nt = 0; nt < a.N / BN; ++nt)
-        for (int kb = 0; kb < nkb; ++kb)
-            for (int n = 0; n < BN; ++n)
-                for (int k = 0; k < HBK; ++k) {
-                    const float w = hi[(size_t)(nt * BN + n) * a.Kp + kb * HBK + k] * scale;
-                    const __half h = __float2half_rn(w);
-                    const __half l = __float2half_rn(w - __half2float(h));
-                    const int chunk = (k >> 3) ^ (n & 7);            // 16-byte chunk = 8 halves
-                    const size_t base = (((size_t)nt * nkb + kb) * 2) * (size_t)BN * HBK;
-                    img[base + (size_t)n * HBK + chunk * 8 + (k & 7)] = h;
-                    img[base + (size_t)BN * HBK + (size_t)n * HBK + chunk * 8 + (k & 7)] = l;
-                }
+    for (size_t i = 0; i < plane; ++i) hi[i] += lo[i];           // == the original fp32 weight, exactly
+    std::vector<__half> img;
+    const float scale = iss_f16_build_image(hi.data(), a.N, a.K, a.Kp, BN, img);
     F16Image im;
     im.inv_scale = 1.f / scale;
     ISS_CUDA_OK(cudaMalloc(&im.d, img.size() * sizeof(__half)));
