@@ -15,8 +15,11 @@
 // stand-in VAD softmax vs 1.3e-6 for the TF32 split -- both at the fp32 oracle's own rounding noise.
 //
 // STATUS: written in round 1 after the GPU budget was spent -- compiles for sm_100a, NOT yet run on hardware.
-// Open points to verify first in round 2 (tools/tc_check.py 3): the packing of 16-bit A operands in tensor
-// memory (assumed: 32-bit column c of lane m holds k = 2c in its low half, k = 2c+1 in its high half).
+// First thing to run in round 2: tools/tc_check.py 0 10; tools/tc_check.py 3 10.  Checked off-line: the
+// instruction-descriptor fields and the dense packing of 16-bit A operands in tensor memory (32-bit column c of
+// lane m holds k = 2c in its low half, k = 2c+1 in its high half) agree with CUTLASS (cute/arch/mma_sm100_desc.hpp,
+// tmem_frg_1sm<a_type, a_type> in cute/atom/mma_traits_sm100.hpp); the weight image with the descriptor
+// convention (tools/f16_image_check.cu, host-only).
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <math.h>
