@@ -618,7 +618,10 @@ struct Tc3Cfg {
 };
 
 // NSETS = 2: two producer warp-sets (warps 0-3 and 5-8, TMEM lane quadrant = warp % 4) alternate k-blocks.
-template <int BN, int SB, int ST, int NSETS>
+// V2 (ISS_B200_TC3_V2=1, prepared for round 2, not yet run on hardware): swizzle key (x + row * OW) & 7 instead of
+// p & 7 (no bank conflicts at image-row wraps: 0.42 -> 0.06 extra wavefronts per wavefront, tests/test_slab_indexing.py)
+// and explicit ld.shared for the slab reads (the generic-pointer form compiles to LD.E.128 + 64-bit address math).
+template <int BN, int SB, int ST, int NSETS, bool V2 = false>
 __global__ void __launch_bounds__(32 * (4 * NSETS + 1), (Tc3Cfg<BN, SB, ST, NSETS>::TMEM_COLS <= 256 ? 2 : 1))
 conv_gemm_tc3_kernel(const ConvArgs a)
 {
@@ -678,12 +681,17 @@ conv_gemm_tc3_kernel(const ConvArgs a)
             const int total = rows * a.W * cpp;
             int p = ptid / cpp, j = ptid - p * cpp;              // chunk ptid, then += PRODUCERS per iteration
             const int dp = Cfg::PRODUCERS / cpp, dj = Cfg::PRODUCERS - dp * cpp;
+            int prow = 0, px = 0;                                // V2: slab row / column of pixel p
+            if constexpr (V2) { prow = p / a.W; px = p - prow * a.W; }
             for (int q = ptid; q < total; q += Cfg::PRODUCERS) {
-                const uint32_t dst = slab_u32 + (uint32_t)p * pix_bytes + (uint32_t)(((j & ~7) | ((j ^ p) & 7)) << 4);
+                const int key = V2 ? (px + prow * a.OW) : p;
+                const uint32_t dst = slab_u32 + (uint32_t)p * pix_bytes + (uint32_t)(((j & ~7) | ((j ^ key) & 7)) << 4);
                 const bool ok = q < avail;
                 cp_async16_u32(dst, src0 + (ok ? (size_t)q * 4 : 0), ok ? 16 : 0);
                 p += dp; j += dj;
-                if (j >= cpp) { j -= cpp; ++p; }
+                if constexpr (V2) px += dp;
+                if (j >= cpp) { j -= cpp; ++p; if constexpr (V2) ++px; }
+                if constexpr (V2) { while (px >= a.W) { px -= a.W; ++prow; } }
             }
             cp_async_commit();
             cp_async_wait<0>();
@@ -693,30 +701,40 @@ conv_gemm_tc3_kernel(const ConvArgs a)
         const long long t_l0 = prof ? clock64() : 0;
         // ============================ A producers ============================
         const int r = quad * 32 + lane;                          // GEMM row = TMEM lane
-        int pix0 = 0;
+        int pix0 = 0, key0 = 0;
         if (r < valid) {
             const int dq = r / a.OW, ow = r - dq * a.OW;
-            pix0 = (dq + KH1 * (int)((q0 + dq) / a.OH - img0)) * a.W + ow;
+            const int srow = dq + KH1 * (int)((q0 + dq) / a.OH - img0);
+            pix0 = srow * a.W + ow;
+            if constexpr (V2) key0 = ow + srow * a.OW;
         }
         int is_c0 = 0, is_ss = 0, is_poff = 0;                   // tap state of the next k-block to load
+        int is_key = 0;                                          // V2: swizzle key offset of that tap
         const uint32_t lane_addr = ((uint32_t)(quad * 32)) << 16;
         uint32_t hi[32], lo[32];
         auto advance = [&]() {
             is_c0 += TBK;
             if (is_c0 == a.C) {
                 is_c0 = 0; ++is_poff;
-                if (++is_ss == a.KW) { is_ss = 0; is_poff += a.W - a.KW; }
+                if constexpr (V2) ++is_key;
+                if (++is_ss == a.KW) { is_ss = 0; is_poff += a.W - a.KW; if constexpr (V2) is_key += a.OW - a.KW; }
             }
         };
         for (int q = 0; q < pset; ++q) advance();
         auto load_split = [&]() {
             const int p = pix0 + is_poff;
             const unsigned char *base = slab + (size_t)p * pix_bytes + is_c0 * 4;
-            const uint32_t x = (uint32_t)(p & 7) << 4;
+            const uint32_t x = (uint32_t)((V2 ? (key0 + is_key) : p) & 7) << 4;
             uint32_t v[32];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const uint4 q = *reinterpret_cast<const uint4 *>(base + (((uint32_t)j << 4) ^ x));
+                uint4 q;
+                if constexpr (V2) {
+                    const uint32_t addr = slab_u32 + (uint32_t)p * pix_bytes + (uint32_t)is_c0 * 4 + (((uint32_t)j << 4) ^ x);
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(addr));
+                } else {
+                    q = *reinterpret_cast<const uint4 *>(base + (((uint32_t)j << 4) ^ x));
+                }
                 v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
             }
 #pragma unroll
@@ -828,11 +846,11 @@ conv_gemm_tc3_kernel(const ConvArgs a)
 constexpr int SMEM_CTA_MAX = 232448;       // 227 KB opt-in limit per CTA
 constexpr int SMEM_HALF_SM = 115712;       // two CTAs per SM: 2 * (x + 1 KB reserved) <= 228 KB
 
-template <int BN, int SB, int ST, int NSETS = 1>
+template <int BN, int SB, int ST, int NSETS = 1, bool V2 = false>
 int launch_tc3(const ConvArgs &a, int slab_bytes, cudaStream_t st)
 {
     using Cfg = Tc3Cfg<BN, SB, ST, NSETS>;
-    auto kern = conv_gemm_tc3_kernel<BN, SB, ST, NSETS>;
+    auto kern = conv_gemm_tc3_kernel<BN, SB, ST, NSETS, V2>;
     static bool configured = false;
     if (!configured) {
         ISS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CTA_MAX));
@@ -881,6 +899,16 @@ int try_launch_slab(ConvArgs &a, cudaStream_t st)
     if (cfg == 1 && a.N % 128 != 0 && Tc3Cfg<64, 4, 6>::FIXED + slab_bytes <= SMEM_CTA_MAX) return launch_tc3<64, 4, 6, 1>(a, slab_bytes, st);
     if (cfg == 2 && a.N % 128 != 0 && Tc3Cfg<64, 4, 6>::FIXED + slab_bytes <= SMEM_CTA_MAX) return launch_tc3<64, 4, 6, 2>(a, slab_bytes, st);
     if (cfg == 2 && a.N % 128 == 0 && Tc3Cfg<128, 3, 4>::FIXED + slab_bytes <= SMEM_CTA_MAX) return launch_tc3<128, 3, 4, 2>(a, slab_bytes, st);
+    static const int v2 = [] { const char *e = getenv("ISS_B200_TC3_V2"); return (e && e[0] == '1') ? 1 : 0; }();      // prepared, not yet validated
+    if (v2) {
+        if (a.N % 128 == 0) {
+            if (Tc3Cfg<128, 4, 4>::FIXED + slab_bytes <= SMEM_CTA_MAX) return launch_tc3<128, 4, 4, 1, true>(a, slab_bytes, st);
+            if (Tc3Cfg<128, 3, 4>::FIXED + slab_bytes <= SMEM_CTA_MAX) return launch_tc3<128, 3, 4, 1, true>(a, slab_bytes, st);
+        } else {
+            if (Tc3Cfg<64, 3, 2>::FIXED + slab_bytes <= SMEM_HALF_SM) return launch_tc3<64, 3, 2, 1, true>(a, slab_bytes, st);
+            if (Tc3Cfg<64, 2, 2>::FIXED + slab_bytes <= SMEM_HALF_SM) return launch_tc3<64, 2, 2, 1, true>(a, slab_bytes, st);
+        }
+    }
     if (a.N % 128 == 0) {
         if (Tc3Cfg<128, 4, 4>::FIXED + slab_bytes <= SMEM_CTA_MAX) return launch_tc3<128, 4, 4>(a, slab_bytes, st);
         if (Tc3Cfg<128, 3, 4>::FIXED + slab_bytes <= SMEM_CTA_MAX) return launch_tc3<128, 3, 4>(a, slab_bytes, st);

@@ -52,20 +52,27 @@ def emulate_tile(x, t, KH, KW, key):
     for r in range(valid):
         dq, ow = divmod(r, OW)
         pix0 = (dq + (KH - 1) * ((q0 + dq) // OH - img0)) * W + ow
+        srow = dq + (KH - 1) * ((q0 + dq) // OH - img0)
+        key0, is_key = ow + srow * OW, 0                      # the V2 kernel carries the key incrementally
         c0 = ss = poff = 0
         for kb in range(KH * KW * C // 32):
             p = pix0 + poff
+            kx = key(p, W, OW) & 7
+            if key is key_rowwrap_free:
+                assert kx == (key0 + is_key) & 7
             for jj in range(8):
-                phys = p * cpp + c0 // 4 + (jj ^ (key(p, W, OW) & 7))
+                phys = p * cpp + c0 // 4 + (jj ^ kx)
                 out[r, kb * 32 + jj * 4:kb * 32 + jj * 4 + 4] = slab[phys]
             c0 += 32
             if c0 == C:
                 c0 = 0
                 poff += 1
+                is_key += 1
                 ss += 1
                 if ss == KW:
                     ss = 0
                     poff += W - KW
+                    is_key += OW - KW
     return q0 * OW, out
 
 
