@@ -141,3 +141,28 @@ def test_bank_conflicts_of_the_two_keys():
     print('extra LDS wavefronts per ideal wavefront: key p&7 = %.3f, row-wrap-free key = %.3f' % (cur, new))
     assert 0.15 < cur < 0.6             # ncu: 43.6 M conflicts / 126 M wavefronts for the whole kernel
     assert new <= 0.25 * cur
+
+
+@pytest.mark.parametrize('W,OW,C,total_px,producers', [(17, 14, 64, 17 * 17, 128), (20, 17, 64, 15 * 20, 128), (7, 5, 64, 29 * 7, 128), (5, 3, 128, 48 * 5, 128), (7, 5, 96, 29 * 7, 256)])
+def test_fill_loop_tracks_row_and_column(W, OW, C, total_px, producers):
+    """The V2 fill keeps (prow, px) of pixel p incrementally (p advances by PRODUCERS / cpp chunks' worth per iteration)."""
+    cpp = C // 4
+    total = total_px * cpp
+    seen = set()
+    for ptid in range(producers):
+        p, j = divmod(ptid, cpp)
+        dp = producers // cpp
+        dj = producers - dp * cpp
+        prow, px = divmod(p, W)
+        q = ptid
+        while q < total:
+            assert (p, j) == divmod(q, cpp) and (prow, px) == divmod(p, W)
+            assert (px + prow * OW) & 7 == key_rowwrap_free(p, W, OW) & 7
+            seen.add(q)
+            p += dp; j += dj; px += dp
+            if j >= cpp:
+                j -= cpp; p += 1; px += 1
+            while px >= W:
+                px -= W; prow += 1
+            q += producers
+    assert len(seen) == total
