@@ -411,6 +411,8 @@ extern "C" int iss_cnn_forward(iss_ctx *ctx, iss_cnn *cnn, const float *d_mspec,
         const int64_t nb = std::min<int64_t>(B, n - b0);
         const float *cur = nullptr;
         int which = 0;
+        bool pool_pending = false;                               // previous pooling layer folded into the next convolution
+        int pool_in_h = 0, pool_in_w = 0;
         for (size_t li = 0; li < cnn->layers.size(); ++li) {
             const Layer &Lr = cnn->layers[li];
             const iss_layer_desc &d = Lr.d;
@@ -429,6 +431,26 @@ extern "C" int iss_cnn_forward(iss_ctx *ctx, iss_cnn *cnn, const float *d_mspec,
             }
             if (d.kind == ISS_LAYER_MAXPOOL) {
                 ISS_REQUIRE(li > 0, ISS_ERR_UNSUPPORTED, "iss_cnn_forward: pooling as first layer is not supported");
+                // ISS_B200_FUSE_POOL=1 (prepared, not yet run on hardware): a 2x2/2 'valid' pooling in front of a
+                // convolution the slab kernel covers is folded into that kernel's slab fill and never launched
+                static const bool fuse_pool = [] { const char *e = getenv("ISS_B200_FUSE_POOL"); return e && e[0] == '1'; }();
+                if (fuse_pool && li + 1 < cnn->layers.size() && d.kh == 2 && d.kw == 2 && d.sh == 2 && d.sw == 2 &&
+                    d.pad_top == 0 && d.pad_left == 0 && Lr.out_h == Lr.in_h / 2 && Lr.out_w == Lr.in_w / 2) {
+                    const Layer &Nx = cnn->layers[li + 1];
+                    if (Nx.d.kind == ISS_LAYER_CONV2D && Nx.d_wt) {
+                        ConvArgs probe = {};
+                        probe.wt_hi = Nx.d_wt; probe.wt_lo = Nx.d_wt + (size_t)Nx.d.cout * Nx.Kp; probe.wt_tiled = Nx.d_wt + 2 * (size_t)Nx.d.cout * Nx.Kp;
+                        probe.Kp = Nx.Kp; probe.N = Nx.d.cout; probe.K = Nx.d.kh * Nx.d.kw * Nx.d.cin;
+                        probe.M = nb * Nx.out_h * Nx.out_w;
+                        probe.H = Nx.in_h; probe.W = Nx.in_w; probe.C = Nx.in_c; probe.OH = Nx.out_h; probe.OW = Nx.out_w;
+                        probe.KH = Nx.d.kh; probe.KW = Nx.d.kw; probe.SH = Nx.d.sh; probe.SW = Nx.d.sw; probe.PT = Nx.d.pad_top; probe.PL = Nx.d.pad_left;
+                        if (Nx.d.pad_bottom == 0 && Nx.d.pad_right == 0 && iss_conv_poolin_supported(probe, iss_get_gemm_mode())) {
+                            pool_pending = true; pool_in_h = Lr.in_h; pool_in_w = Lr.in_w;
+                            if (prof) { ISS_CUDA_OK(cudaEventRecord(cnn->prof_ev[cnn->prof_used + 1], st)); cnn->prof_used += 2; }
+                            continue;                            // `cur` stays the un-pooled tensor, the ping-pong buffer is not flipped
+                        }
+                    }
+                }
                 const int64_t total = nb * Lr.out_h * Lr.out_w * Lr.out_c;
                 maxpool_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(cur, dst, total, Lr.in_h, Lr.in_w, Lr.in_c,
                     Lr.out_h, Lr.out_w, d.kh, d.kw, d.sh, d.sw, d.pad_top, d.pad_left);
@@ -486,6 +508,7 @@ extern "C" int iss_cnn_forward(iss_ctx *ctx, iss_cnn *cnn, const float *d_mspec,
                     }
                 } else {
                     a.in = cur;
+                    if (pool_pending) { a.pool_in = 1; a.inH = pool_in_h; a.inW = pool_in_w; pool_pending = false; }
                     rc = iss_launch_conv(a, false, st);
                 }
                 if (rc != ISS_OK) return rc;

@@ -28,6 +28,9 @@ struct ConvArgs {
     int slab_rows;          // input rows the slab is sized for
     int64_t in_elems;       // floats in `in` (loads past the end are zero-filled)
     unsigned long long *prof;   // ISS_B200_TC_PROF=1: per-role wait-cycle counters (experiments only)
+    // fused 2x2/2 'valid' max-pooling of the INPUT (ISS_B200_FUSE_POOL=1, slab kernel only): `in` is the un-pooled
+    // NHWC tensor [n_img][inH][inW][C]; H = inH / 2 and W = inW / 2 are the pooled dims the convolution sees
+    int pool_in, inH, inW;
 };
 
 #define ISS_GEMM_FP32  0      /* fp32 CUDA cores (conv_gemm.cu) */
@@ -41,6 +44,8 @@ struct ConvArgs {
 extern "C" int iss_get_gemm_mode(void);
 bool iss_conv_tc_eligible(const ConvArgs &a);
 int iss_launch_conv_tc(const ConvArgs &a, int mode, cudaStream_t st);
+// true if a convolution described by `a` (pooled dims, weights set) can take its input through the fused pooling path
+bool iss_conv_poolin_supported(const ConvArgs &a, int mode);
 // W[K][N] -> device buffer: [2][N][Kp] row-major (hi, lo) then the tiled/pre-swizzled image [2*N*Kp]; Kp = K rounded up to 32
 int iss_prepare_tc_weights(const float *h_w, int K, int N, float **d_out, int *Kp_out);
 

@@ -621,7 +621,10 @@ struct Tc3Cfg {
 // V2 (ISS_B200_TC3_V2=1, prepared for round 2, not yet run on hardware): swizzle key (x + row * OW) & 7 instead of
 // p & 7 (no bank conflicts at image-row wraps: 0.42 -> 0.06 extra wavefronts per wavefront, tests/test_slab_indexing.py)
 // and explicit ld.shared for the slab reads (the generic-pointer form compiles to LD.E.128 + 64-bit address math).
-template <int BN, int SB, int ST, int NSETS, bool V2 = false>
+// POOLIN (ISS_B200_FUSE_POOL=1, implies V2; prepared, not yet run on hardware): the slab is filled with the 2x2/2
+// max-pooling of the un-pooled input tensor, so the pooling layer in front of this convolution is never launched
+// and its output never written (same comparison order and NaN propagation as maxpool_nhwc_kernel).
+template <int BN, int SB, int ST, int NSETS, bool V2 = false, bool POOLIN = false>
 __global__ void __launch_bounds__(32 * (4 * NSETS + 1), (Tc3Cfg<BN, SB, ST, NSETS>::TMEM_COLS <= 256 ? 2 : 1))
 conv_gemm_tc3_kernel(const ConvArgs a)
 {
@@ -678,20 +681,53 @@ conv_gemm_tc3_kernel(const ConvArgs a)
             const int64_t first = g0 * a.W * a.C;                // element offset of the slab in `in`
             const float *src0 = a.in + first;
             const int64_t avail = (a.in_elems - first) >> 2;     // chunks that exist past `first`
+            (void)src0; (void)avail;
             const int total = rows * a.W * cpp;
             int p = ptid / cpp, j = ptid - p * cpp;              // chunk ptid, then += PRODUCERS per iteration
             const int dp = Cfg::PRODUCERS / cpp, dj = Cfg::PRODUCERS - dp * cpp;
             int prow = 0, px = 0;                                // V2: slab row / column of pixel p
             if constexpr (V2) { prow = p / a.W; px = p - prow * a.W; }
-            for (int q = ptid; q < total; q += Cfg::PRODUCERS) {
-                const int key = V2 ? (px + prow * a.OW) : p;
-                const uint32_t dst = slab_u32 + (uint32_t)p * pix_bytes + (uint32_t)(((j & ~7) | ((j ^ key) & 7)) << 4);
-                const bool ok = q < avail;
-                cp_async16_u32(dst, src0 + (ok ? (size_t)q * 4 : 0), ok ? 16 : 0);
-                p += dp; j += dj;
-                if constexpr (V2) px += dp;
-                if (j >= cpp) { j -= cpp; ++p; if constexpr (V2) ++px; }
-                if constexpr (V2) { while (px >= a.W) { px -= a.W; ++prow; } }
+            if constexpr (POOLIN) {
+                static_assert(!POOLIN || V2, "POOLIN builds on the V2 row/column tracking");
+                const int64_t Gtot = a.M / ((int64_t)a.OH * a.OW) * a.H;          // pooled input rows in the batch
+                int64_t img = (g0 + prow) / a.H;
+                int prr = (int)((g0 + prow) - img * a.H);                          // pooled row inside its image
+                const size_t row_stride = (size_t)a.inW * a.C;
+                for (int q = ptid; q < total; q += Cfg::PRODUCERS) {
+                    const int key = px + prow * a.OW;
+                    const uint32_t dst = slab_u32 + (uint32_t)p * pix_bytes + (uint32_t)(((j & ~7) | ((j ^ key) & 7)) << 4);
+                    float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (g0 + prow < Gtot) {
+                        const float *s0 = a.in + ((size_t)(img * a.inH + 2 * prr) * a.inW + 2 * px) * a.C + j * 4;
+                        const float4 v00 = __ldg(reinterpret_cast<const float4 *>(s0));
+                        const float4 v01 = __ldg(reinterpret_cast<const float4 *>(s0 + a.C));
+                        const float4 v10 = __ldg(reinterpret_cast<const float4 *>(s0 + row_stride));
+                        const float4 v11 = __ldg(reinterpret_cast<const float4 *>(s0 + row_stride + a.C));
+                        auto mx = [](float best, float v) { return (v > best || v != v) ? v : best; };   // as maxpool_nhwc_kernel
+                        m.x = mx(mx(mx(mx(-INFINITY, v00.x), v01.x), v10.x), v11.x);
+                        m.y = mx(mx(mx(mx(-INFINITY, v00.y), v01.y), v10.y), v11.y);
+                        m.z = mx(mx(mx(mx(-INFINITY, v00.z), v01.z), v10.z), v11.z);
+                        m.w = mx(mx(mx(mx(-INFINITY, v00.w), v01.w), v10.w), v11.w);
+                    }
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(m.x), "f"(m.y), "f"(m.z), "f"(m.w) : "memory");
+                    p += dp; j += dj; px += dp;
+                    if (j >= cpp) { j -= cpp; ++p; ++px; }
+                    while (px >= a.W) {
+                        px -= a.W; ++prow;
+                        if (++prr == a.H) { prr = 0; ++img; }
+                    }
+                }
+            } else {
+                for (int q = ptid; q < total; q += Cfg::PRODUCERS) {
+                    const int key = V2 ? (px + prow * a.OW) : p;
+                    const uint32_t dst = slab_u32 + (uint32_t)p * pix_bytes + (uint32_t)(((j & ~7) | ((j ^ key) & 7)) << 4);
+                    const bool ok = q < avail;
+                    cp_async16_u32(dst, src0 + (ok ? (size_t)q * 4 : 0), ok ? 16 : 0);
+                    p += dp; j += dj;
+                    if constexpr (V2) px += dp;
+                    if (j >= cpp) { j -= cpp; ++p; if constexpr (V2) ++px; }
+                    if constexpr (V2) { while (px >= a.W) { px -= a.W; ++prow; } }
+                }
             }
             cp_async_commit();
             cp_async_wait<0>();
@@ -846,11 +882,11 @@ conv_gemm_tc3_kernel(const ConvArgs a)
 constexpr int SMEM_CTA_MAX = 232448;       // 227 KB opt-in limit per CTA
 constexpr int SMEM_HALF_SM = 115712;       // two CTAs per SM: 2 * (x + 1 KB reserved) <= 228 KB
 
-template <int BN, int SB, int ST, int NSETS = 1, bool V2 = false>
+template <int BN, int SB, int ST, int NSETS = 1, bool V2 = false, bool POOLIN = false>
 int launch_tc3(const ConvArgs &a, int slab_bytes, cudaStream_t st)
 {
     using Cfg = Tc3Cfg<BN, SB, ST, NSETS>;
-    auto kern = conv_gemm_tc3_kernel<BN, SB, ST, NSETS, V2>;
+    auto kern = conv_gemm_tc3_kernel<BN, SB, ST, NSETS, V2, POOLIN>;
     static bool configured = false;
     if (!configured) {
         ISS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CTA_MAX));
@@ -899,6 +935,16 @@ int try_launch_slab(ConvArgs &a, cudaStream_t st)
     if (cfg == 1 && a.N % 128 != 0 && Tc3Cfg<64, 4, 6>::FIXED + slab_bytes <= SMEM_CTA_MAX) return launch_tc3<64, 4, 6, 1>(a, slab_bytes, st);
     if (cfg == 2 && a.N % 128 != 0 && Tc3Cfg<64, 4, 6>::FIXED + slab_bytes <= SMEM_CTA_MAX) return launch_tc3<64, 4, 6, 2>(a, slab_bytes, st);
     if (cfg == 2 && a.N % 128 == 0 && Tc3Cfg<128, 3, 4>::FIXED + slab_bytes <= SMEM_CTA_MAX) return launch_tc3<128, 3, 4, 2>(a, slab_bytes, st);
+    if (a.pool_in) {                                             // fused input pooling: POOLIN instantiations only
+        if (a.N % 128 == 0) {
+            if (Tc3Cfg<128, 4, 4>::FIXED + slab_bytes <= SMEM_CTA_MAX) return launch_tc3<128, 4, 4, 1, true, true>(a, slab_bytes, st);
+            if (Tc3Cfg<128, 3, 4>::FIXED + slab_bytes <= SMEM_CTA_MAX) return launch_tc3<128, 3, 4, 1, true, true>(a, slab_bytes, st);
+        } else {
+            if (Tc3Cfg<64, 3, 2>::FIXED + slab_bytes <= SMEM_HALF_SM) return launch_tc3<64, 3, 2, 1, true, true>(a, slab_bytes, st);
+            if (Tc3Cfg<64, 2, 2>::FIXED + slab_bytes <= SMEM_HALF_SM) return launch_tc3<64, 2, 2, 1, true, true>(a, slab_bytes, st);
+        }
+        return 1;
+    }
     static const int v2 = [] { const char *e = getenv("ISS_B200_TC3_V2"); return (e && e[0] == '1') ? 1 : 0; }();      // prepared, not yet validated
     if (v2) {
         if (a.N % 128 == 0) {
@@ -990,6 +1036,20 @@ bool iss_conv_tc_eligible(const ConvArgs &a)
     return a.wt_hi && a.wt_lo && a.wt_tiled && a.Kp > 0 && a.C % 32 == 0 && a.K % 32 == 0 && a.N % 32 == 0 && a.N >= 32;
 }
 
+// Mirrors the checks of try_launch_slab + the POOLIN dispatch above (kept next to them on purpose).
+bool iss_conv_poolin_supported(const ConvArgs &a, int mode)
+{
+    if (mode != ISS_GEMM_TC_TS || !iss_conv_tc_eligible(a)) return false;
+    if (a.SH != 1 || a.SW != 1 || a.PT != 0 || a.PL != 0 || a.KH * a.KW <= 1) return false;
+    if (a.OH != a.H - a.KH + 1 || a.OW != a.W - a.KW + 1 || a.OW > TBM || a.Kp != a.K || a.N % 64 != 0) return false;
+    const int R = TBM / a.OW;
+    const int cross = (R - 1) / a.OH + 1;
+    int slab_bytes = (R + (a.KH - 1) * (1 + cross)) * a.W * a.C * 4;
+    if (slab_bytes < 32768) slab_bytes = 32768;
+    if (a.N % 128 == 0) return Tc3Cfg<128, 3, 4>::FIXED + slab_bytes <= SMEM_CTA_MAX;
+    return Tc3Cfg<64, 2, 2>::FIXED + slab_bytes <= SMEM_HALF_SM;
+}
+
 int iss_launch_conv_tc(const ConvArgs &a_in, int mode, cudaStream_t st)
 {
     static const int dbg = [] { const char *e = getenv("ISS_B200_TC_DEBUG"); return e ? atoi(e) : 0; }();   // timing experiments: 1 = same-address gathers, 2 = L1-allocating gathers
@@ -1000,6 +1060,7 @@ int iss_launch_conv_tc(const ConvArgs &a_in, int mode, cudaStream_t st)
         if (rc != 1) return rc;
     }
     const bool ts = (mode == ISS_GEMM_TC_TS || mode == ISS_GEMM_TC_F16);
+    ISS_REQUIRE(!a.pool_in || mode == ISS_GEMM_TC_TS, ISS_ERR_UNSUPPORTED, "conv_tc: fused input pooling needs engine 2");
     // BN: the widest of {256,128,64,32} dividing N
     // two accumulators per tile (main + correction) => BN <= 128 (2 x 128 + A ring <= 512 TMEM columns)
     if (ts) {
@@ -1009,10 +1070,11 @@ int iss_launch_conv_tc(const ConvArgs &a_in, int mode, cudaStream_t st)
             if (a.N % 64 == 0) return launch_tc2<64, 2, 4, 6, 2>(a, st);     // 129 KB smem (=> ~96 KB L1), 512 TMEM cols
         }
         static const int slab = [] { const char *e = getenv("ISS_B200_TC_SLAB"); return (e && e[0] == '0') ? 0 : 1; }();
-        if (slab) {                                                      // un-padded stride-1 KHxKW convs: input slab in smem
+        if (slab || a.pool_in) {                                         // un-padded stride-1 KHxKW convs: input slab in smem
             const int rc = try_launch_slab(a, st);
             if (rc != 1) return rc;
         }
+        ISS_REQUIRE(!a.pool_in, ISS_ERR_UNSUPPORTED, "conv_tc: fused input pooling needs the slab kernel");
         if (a.N % 128 == 0) return launch_tc2<128, 4, 4, 4>(a, st);      // 193 KB smem, 512 TMEM cols (2x128 acc + 4 A stages), 1 CTA/SM
         if (a.N % 64 == 0) return launch_tc2<64, 3, 3, 2>(a, st);        //  97 KB smem, 256 TMEM cols, 2 CTAs/SM
         return launch_tc2<32, 3, 4, 3>(a, st);                            //  81 KB smem, 256 TMEM cols
