@@ -1065,7 +1065,7 @@ int iss_launch_conv_tc(const ConvArgs &a_in, int mode, cudaStream_t st)
     // two accumulators per tile (main + correction) => BN <= 128 (2 x 128 + A ring <= 512 TMEM columns)
     if (ts) {
         static const int two_sets = [] { const char *e = getenv("ISS_B200_TC_SETS"); return (e && e[0] == '2') ? 1 : 0; }();
-        if (two_sets) {
+        if (two_sets && !a.pool_in) {
             if (a.N % 128 == 0) return launch_tc2<128, 2, 4, 4, 2>(a, st);   // 193 KB smem, 512 TMEM cols
             if (a.N % 64 == 0) return launch_tc2<64, 2, 4, 6, 2>(a, st);     // 129 KB smem (=> ~96 KB L1), 512 TMEM cols
         }
