@@ -196,6 +196,89 @@ conv_first_direct_kernel(const FirstArgs a)
     }
 }
 
+// V2 (ISS_B200_FIRST_V2=1; prepared, not yet run on hardware): the kernel above is bound by shared-memory bandwidth, not
+// FMAs (per tap and warp 6 LSU wavefronts for 16 FMA instructions), so this variant reads the FIRST_P + KW - 1 inputs of a
+// filter row once into registers and reuses them for every tap of that row.  Same (kh, kw) FMA order => identical bits.
+constexpr int FIRST_KWMAX = 8;
+__global__ void __launch_bounds__(256)
+conv_first_direct_v2_kernel(const FirstArgs a)
+{
+    extern __shared__ __align__(16) float fsm[];
+    float *ws = fsm;                                   // [K][Cout]
+    float *xs = fsm + a.KH * a.KW * a.Cout;            // [Hp][Wp] (+ slack), zero border
+    const int tid = threadIdx.x;
+    const int CQ = a.Cout >> 2, streams = 256 / CQ;
+    const int c4 = tid % CQ, stream = tid / CQ;
+    const int K = a.KH * a.KW;
+    for (int i = tid; i < K * a.Cout; i += 256) ws[i] = a.w[i];
+    const int xs_len = a.Hp * a.Wp + FIRST_P * a.SW + a.KW;
+    float eb[4], es1[4], et1[4], es2[4], et2[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int c = c4 * 4 + q;
+        eb[q] = (a.flags & ISS_F_BIAS) ? a.bias[c] : 0.f;
+        es1[q] = (a.flags & ISS_F_AFFINE_PRE) ? a.pre_scale[c] : 1.f;  et1[q] = (a.flags & ISS_F_AFFINE_PRE) ? a.pre_shift[c] : 0.f;
+        es2[q] = (a.flags & ISS_F_AFFINE_POST) ? a.post_scale[c] : 1.f; et2[q] = (a.flags & ISS_F_AFFINE_POST) ? a.post_shift[c] : 0.f;
+    }
+    const int nblk = (a.OW + FIRST_P - 1) / FIRST_P;
+    const int G = a.OH * nblk;
+    for (int64_t img = blockIdx.x; img < a.n; img += gridDim.x) {
+        __syncthreads();                               // previous patch fully consumed (and ws visible)
+        for (int i = tid; i < xs_len; i += 256) xs[i] = 0.f;
+        __syncthreads();
+        const float mu = a.mu[img], sg = a.sigma[img];
+        const float *src = a.mspec + (int64_t)a.row0[img] * a.ld;
+        for (int e = tid; e < a.H * a.W; e += 256) {
+            const int r = e / a.W, c = e - r * a.W;
+            xs[(r + a.PT) * a.Wp + c + a.PL] = __fdiv_rn(__fsub_rn(__ldg(src + (int64_t)r * a.ld + c), mu), sg);
+        }
+        __syncthreads();
+        float *out_img = a.out + img * ((int64_t)a.OH * a.OW * a.Cout);
+        for (int g = stream; g < G; g += streams) {
+            const int oh = g / nblk, ow0 = (g - oh * nblk) * FIRST_P;
+            float acc[FIRST_P][4];
+#pragma unroll
+            for (int p = 0; p < FIRST_P; ++p)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[p][q] = 0.f;
+            for (int r = 0; r < a.KH; ++r) {                     // SW == 1, KW <= FIRST_KWMAX (checked by the launcher)
+                const float *xrow = xs + (oh * a.SH + r) * a.Wp + ow0;
+                const float *wrow = ws + (r * a.KW) * a.Cout + c4 * 4;
+                float xv[FIRST_P + FIRST_KWMAX - 1];               // the row's inputs once, reused by every tap
+#pragma unroll
+                for (int i = 0; i < FIRST_P + FIRST_KWMAX - 1; ++i) xv[i] = (i < FIRST_P + a.KW - 1) ? xrow[i] : 0.f;
+#pragma unroll
+                for (int t = 0; t < FIRST_KWMAX; ++t) {
+                    if (t < a.KW) {
+                        const float4 w4 = *reinterpret_cast<const float4 *>(wrow + t * a.Cout);
+#pragma unroll
+                        for (int p = 0; p < FIRST_P; ++p) {
+                            const float x = xv[p + t];
+                            acc[p][0] = fmaf(x, w4.x, acc[p][0]); acc[p][1] = fmaf(x, w4.y, acc[p][1]);
+                            acc[p][2] = fmaf(x, w4.z, acc[p][2]); acc[p][3] = fmaf(x, w4.w, acc[p][3]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < FIRST_P; ++p) {
+                if (ow0 + p >= a.OW) continue;
+                float y[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float v = acc[p][q] + eb[q];
+                    if (a.flags & ISS_F_AFFINE_PRE) v = fmaf(v, es1[q], et1[q]);
+                    if (a.flags & ISS_F_RELU) v = fmaxf(v, 0.f);
+                    if (a.flags & ISS_F_SIGMOID) v = 1.f / (1.f + expf(-v));
+                    if (a.flags & ISS_F_AFFINE_POST) v = fmaf(v, es2[q], et2[q]);
+                    y[q] = v;
+                }
+                *reinterpret_cast<float4 *>(out_img + ((int64_t)oh * a.OW + ow0 + p) * a.Cout + c4 * 4) = make_float4(y[0], y[1], y[2], y[3]);
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------ max pooling (NHWC)
 __global__ void __launch_bounds__(256)
 maxpool_nhwc_kernel(const float *__restrict__ in, float *__restrict__ out, int64_t total, int H, int W, int C,
@@ -498,6 +581,15 @@ extern "C" int iss_cnn_forward(iss_ctx *ctx, iss_cnn *cnn, const float *d_mspec,
                             configured = true;
                         }
                         const unsigned grid = (unsigned)std::min<int64_t>(nb, (int64_t)ctx->sm_count * 8);
+                        static const bool first_v2 = [] { const char *e = getenv("ISS_B200_FIRST_V2"); return e && e[0] == '1'; }();
+                        if (first_v2 && d.sw == 1 && d.kw <= FIRST_KWMAX) {
+                            static bool configured2 = false;
+                            if (!configured2) {
+                                ISS_CUDA_OK(cudaFuncSetAttribute(conv_first_direct_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                                configured2 = true;
+                            }
+                            conv_first_direct_v2_kernel<<<grid, 256, smem, st>>>(f);
+                        } else
                         conv_first_direct_kernel<<<grid, 256, smem, st>>>(f);
                         ISS_CUDA_OK(cudaGetLastError());
                         iss_count_launch();
