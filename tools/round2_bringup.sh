@@ -10,6 +10,7 @@ run timeout 100 python tools/tc_check.py 2 10                                # v
 run ISS_B200_TC3_V2=1 timeout 100 python tools/tc_check.py 2 10              # conflict-free swizzle key + ld.shared
 run ISS_B200_TC3_V2=1 ISS_B200_FUSE_POOL=1 timeout 100 python tools/tc_check.py 2 10
 run ISS_B200_FUSE_POOL=1 timeout 100 python tools/tc_check.py 2 10
+run ISS_B200_FIRST_V2=1 timeout 100 python tools/tc_check.py 2 10            # first layer: row inputs kept in registers
 run timeout 100 python tools/tc_check.py 3 10                                # fp16-split engine
 run ISS_B200_FUSE_POOL=1 timeout 100 python tools/tc_check.py 3 10
 ( cd tools && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o ../gpurun_out/umma_contention_bench umma_contention_bench.cu ) && timeout 120 gpurun_out/umma_contention_bench
