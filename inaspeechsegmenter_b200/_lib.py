@@ -35,8 +35,8 @@ LAYER_CONV2D, LAYER_DENSE, LAYER_MAXPOOL = 1, 2, 3
 F_BIAS, F_AFFINE_PRE, F_RELU, F_AFFINE_POST, F_SOFTMAX, F_SIGMOID = 1, 2, 4, 8, 16, 32
 PCM_F32, PCM_S16 = 0, 1
 FFT_FP32, FFT_FP64 = 0, 1
-GEMM_FP32, GEMM_TC_SS, GEMM_TC_TS = 0, 1, 2
-GEMM_TC_F16_EXPERIMENTAL = 3          # csrc/conv_gemm_tc_f16.cu: not validated on hardware yet
+GEMM_FP32, GEMM_TC_TS, GEMM_TC_F16 = 0, 2, 3     # fp32 CUDA cores | 3xTF32 tcgen05 | fp16-split tcgen05 (default)
+ABI_VERSION = 2                       # == ISS_ABI_VERSION in include/iss_b200.h
 
 # name -> (restype, argtypes); must list every symbol include/iss_b200.h declares
 _vp, _i, _i64, _d = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_double
@@ -101,10 +101,15 @@ def load(build_if_missing=True):
             raise IssError('libiss_b200.so is not built (run `python -m inaspeechsegmenter_b200._build`); '
                            'there is no CPU fallback')
         _build.build()
+    elif build_if_missing and _build.needs_build() and os.access(_build.NVCC, os.X_OK):
+        _build.build()                   # sources newer than the library: never load a stale ABI silently
     lib = _c.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is missing
         fn.restype, fn.argtypes = res, args
+    if lib.iss_version() != ABI_VERSION:
+        raise IssError('libiss_b200.so has ABI version %d, this package binds version %d: rebuild it '
+                       '(python -m inaspeechsegmenter_b200._build --force)' % (lib.iss_version(), ABI_VERSION))
     _LIB = lib
     return lib
 

@@ -196,89 +196,6 @@ conv_first_direct_kernel(const FirstArgs a)
     }
 }
 
-// V2 (ISS_B200_FIRST_V2=1; prepared, not yet run on hardware): the kernel above is bound by shared-memory bandwidth, not
-// FMAs (per tap and warp 6 LSU wavefronts for 16 FMA instructions), so this variant reads the FIRST_P + KW - 1 inputs of a
-// filter row once into registers and reuses them for every tap of that row.  Same (kh, kw) FMA order => identical bits.
-constexpr int FIRST_KWMAX = 8;
-__global__ void __launch_bounds__(256)
-conv_first_direct_v2_kernel(const FirstArgs a)
-{
-    extern __shared__ __align__(16) float fsm[];
-    float *ws = fsm;                                   // [K][Cout]
-    float *xs = fsm + a.KH * a.KW * a.Cout;            // [Hp][Wp] (+ slack), zero border
-    const int tid = threadIdx.x;
-    const int CQ = a.Cout >> 2, streams = 256 / CQ;
-    const int c4 = tid % CQ, stream = tid / CQ;
-    const int K = a.KH * a.KW;
-    for (int i = tid; i < K * a.Cout; i += 256) ws[i] = a.w[i];
-    const int xs_len = a.Hp * a.Wp + FIRST_P * a.SW + a.KW;
-    float eb[4], es1[4], et1[4], es2[4], et2[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int c = c4 * 4 + q;
-        eb[q] = (a.flags & ISS_F_BIAS) ? a.bias[c] : 0.f;
-        es1[q] = (a.flags & ISS_F_AFFINE_PRE) ? a.pre_scale[c] : 1.f;  et1[q] = (a.flags & ISS_F_AFFINE_PRE) ? a.pre_shift[c] : 0.f;
-        es2[q] = (a.flags & ISS_F_AFFINE_POST) ? a.post_scale[c] : 1.f; et2[q] = (a.flags & ISS_F_AFFINE_POST) ? a.post_shift[c] : 0.f;
-    }
-    const int nblk = (a.OW + FIRST_P - 1) / FIRST_P;
-    const int G = a.OH * nblk;
-    for (int64_t img = blockIdx.x; img < a.n; img += gridDim.x) {
-        __syncthreads();                               // previous patch fully consumed (and ws visible)
-        for (int i = tid; i < xs_len; i += 256) xs[i] = 0.f;
-        __syncthreads();
-        const float mu = a.mu[img], sg = a.sigma[img];
-        const float *src = a.mspec + (int64_t)a.row0[img] * a.ld;
-        for (int e = tid; e < a.H * a.W; e += 256) {
-            const int r = e / a.W, c = e - r * a.W;
-            xs[(r + a.PT) * a.Wp + c + a.PL] = __fdiv_rn(__fsub_rn(__ldg(src + (int64_t)r * a.ld + c), mu), sg);
-        }
-        __syncthreads();
-        float *out_img = a.out + img * ((int64_t)a.OH * a.OW * a.Cout);
-        for (int g = stream; g < G; g += streams) {
-            const int oh = g / nblk, ow0 = (g - oh * nblk) * FIRST_P;
-            float acc[FIRST_P][4];
-#pragma unroll
-            for (int p = 0; p < FIRST_P; ++p)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) acc[p][q] = 0.f;
-            for (int r = 0; r < a.KH; ++r) {                     // SW == 1, KW <= FIRST_KWMAX (checked by the launcher)
-                const float *xrow = xs + (oh * a.SH + r) * a.Wp + ow0;
-                const float *wrow = ws + (r * a.KW) * a.Cout + c4 * 4;
-                float xv[FIRST_P + FIRST_KWMAX - 1];               // the row's inputs once, reused by every tap
-#pragma unroll
-                for (int i = 0; i < FIRST_P + FIRST_KWMAX - 1; ++i) xv[i] = (i < FIRST_P + a.KW - 1) ? xrow[i] : 0.f;
-#pragma unroll
-                for (int t = 0; t < FIRST_KWMAX; ++t) {
-                    if (t < a.KW) {
-                        const float4 w4 = *reinterpret_cast<const float4 *>(wrow + t * a.Cout);
-#pragma unroll
-                        for (int p = 0; p < FIRST_P; ++p) {
-                            const float x = xv[p + t];
-                            acc[p][0] = fmaf(x, w4.x, acc[p][0]); acc[p][1] = fmaf(x, w4.y, acc[p][1]);
-                            acc[p][2] = fmaf(x, w4.z, acc[p][2]); acc[p][3] = fmaf(x, w4.w, acc[p][3]);
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int p = 0; p < FIRST_P; ++p) {
-                if (ow0 + p >= a.OW) continue;
-                float y[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float v = acc[p][q] + eb[q];
-                    if (a.flags & ISS_F_AFFINE_PRE) v = fmaf(v, es1[q], et1[q]);
-                    if (a.flags & ISS_F_RELU) v = fmaxf(v, 0.f);
-                    if (a.flags & ISS_F_SIGMOID) v = 1.f / (1.f + expf(-v));
-                    if (a.flags & ISS_F_AFFINE_POST) v = fmaf(v, es2[q], et2[q]);
-                    y[q] = v;
-                }
-                *reinterpret_cast<float4 *>(out_img + ((int64_t)oh * a.OW + ow0 + p) * a.Cout + c4 * 4) = make_float4(y[0], y[1], y[2], y[3]);
-            }
-        }
-    }
-}
-
 // ------------------------------------------------------------------ max pooling (NHWC)
 __global__ void __launch_bounds__(256)
 maxpool_nhwc_kernel(const float *__restrict__ in, float *__restrict__ out, int64_t total, int H, int W, int C,
@@ -300,6 +217,34 @@ maxpool_nhwc_kernel(const float *__restrict__ in, float *__restrict__ out, int64
             if (iw < 0 || iw >= W) continue;
             const float v = in[((img * H + ih) * W + iw) * C + c];
             best = (v > best || v != v) ? v : best;        // NaN propagates like TF's max
+        }
+    }
+    out[i] = best;
+}
+
+// Four channels per thread (C % 4 == 0): 16-byte loads / stores, same window order and NaN rule as above.
+// The pooling layers are pure HBM traffic (218 KB in / 53 KB out per patch for the first one).
+__global__ void __launch_bounds__(256)
+maxpool_nhwc_vec4_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, int64_t total4, int H, int W, int C4,
+                         int OH, int OW, int KH, int KW, int SH, int SW, int PT, int PL)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;       // over [img][oh][ow][c / 4]
+    if (i >= total4) return;
+    const int c = (int)(i % C4);
+    int64_t r = i / C4;
+    const int ow = (int)(r % OW); r /= OW;
+    const int oh = (int)(r % OH);
+    const int64_t img = r / OH;
+    float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    auto mx = [](float b, float v) { return (v > b || v != v) ? v : b; };
+    for (int y = 0; y < KH; ++y) {
+        const int ih = oh * SH - PT + y;
+        if (ih < 0 || ih >= H) continue;
+        for (int x = 0; x < KW; ++x) {
+            const int iw = ow * SW - PL + x;
+            if (iw < 0 || iw >= W) continue;
+            const float4 v = __ldg(in + ((img * H + ih) * W + iw) * C4 + c);
+            best.x = mx(best.x, v.x); best.y = mx(best.y, v.y); best.z = mx(best.z, v.z); best.w = mx(best.w, v.w);
         }
     }
     out[i] = best;
@@ -494,8 +439,6 @@ extern "C" int iss_cnn_forward(iss_ctx *ctx, iss_cnn *cnn, const float *d_mspec,
         const int64_t nb = std::min<int64_t>(B, n - b0);
         const float *cur = nullptr;
         int which = 0;
-        bool pool_pending = false;                               // previous pooling layer folded into the next convolution
-        int pool_in_h = 0, pool_in_w = 0;
         for (size_t li = 0; li < cnn->layers.size(); ++li) {
             const Layer &Lr = cnn->layers[li];
             const iss_layer_desc &d = Lr.d;
@@ -514,29 +457,14 @@ extern "C" int iss_cnn_forward(iss_ctx *ctx, iss_cnn *cnn, const float *d_mspec,
             }
             if (d.kind == ISS_LAYER_MAXPOOL) {
                 ISS_REQUIRE(li > 0, ISS_ERR_UNSUPPORTED, "iss_cnn_forward: pooling as first layer is not supported");
-                // ISS_B200_FUSE_POOL=1 (prepared, not yet run on hardware): a 2x2/2 'valid' pooling in front of a
-                // convolution the slab kernel covers is folded into that kernel's slab fill and never launched
-                static const bool fuse_pool = [] { const char *e = getenv("ISS_B200_FUSE_POOL"); return e && e[0] == '1'; }();
-                if (fuse_pool && li + 1 < cnn->layers.size() && d.kh == 2 && d.kw == 2 && d.sh == 2 && d.sw == 2 &&
-                    d.pad_top == 0 && d.pad_left == 0 && Lr.out_h == Lr.in_h / 2 && Lr.out_w == Lr.in_w / 2) {
-                    const Layer &Nx = cnn->layers[li + 1];
-                    if (Nx.d.kind == ISS_LAYER_CONV2D && Nx.d_wt) {
-                        ConvArgs probe = {};
-                        probe.wt_hi = Nx.d_wt; probe.wt_lo = Nx.d_wt + (size_t)Nx.d.cout * Nx.Kp; probe.wt_tiled = Nx.d_wt + 2 * (size_t)Nx.d.cout * Nx.Kp;
-                        probe.Kp = Nx.Kp; probe.N = Nx.d.cout; probe.K = Nx.d.kh * Nx.d.kw * Nx.d.cin;
-                        probe.M = nb * Nx.out_h * Nx.out_w;
-                        probe.H = Nx.in_h; probe.W = Nx.in_w; probe.C = Nx.in_c; probe.OH = Nx.out_h; probe.OW = Nx.out_w;
-                        probe.KH = Nx.d.kh; probe.KW = Nx.d.kw; probe.SH = Nx.d.sh; probe.SW = Nx.d.sw; probe.PT = Nx.d.pad_top; probe.PL = Nx.d.pad_left;
-                        if (Nx.d.pad_bottom == 0 && Nx.d.pad_right == 0 && iss_conv_poolin_supported(probe, iss_get_gemm_mode())) {
-                            pool_pending = true; pool_in_h = Lr.in_h; pool_in_w = Lr.in_w;
-                            if (prof) { ISS_CUDA_OK(cudaEventRecord(cnn->prof_ev[cnn->prof_used + 1], st)); cnn->prof_used += 2; }
-                            continue;                            // `cur` stays the un-pooled tensor, the ping-pong buffer is not flipped
-                        }
-                    }
-                }
                 const int64_t total = nb * Lr.out_h * Lr.out_w * Lr.out_c;
-                maxpool_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(cur, dst, total, Lr.in_h, Lr.in_w, Lr.in_c,
-                    Lr.out_h, Lr.out_w, d.kh, d.kw, d.sh, d.sw, d.pad_top, d.pad_left);
+                if (Lr.in_c % 4 == 0)
+                    maxpool_nhwc_vec4_kernel<<<(unsigned)((total / 4 + 255) / 256), 256, 0, st>>>(
+                        reinterpret_cast<const float4 *>(cur), reinterpret_cast<float4 *>(dst), total / 4, Lr.in_h, Lr.in_w, Lr.in_c / 4,
+                        Lr.out_h, Lr.out_w, d.kh, d.kw, d.sh, d.sw, d.pad_top, d.pad_left);
+                else
+                    maxpool_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(cur, dst, total, Lr.in_h, Lr.in_w, Lr.in_c,
+                        Lr.out_h, Lr.out_w, d.kh, d.kw, d.sh, d.sw, d.pad_top, d.pad_left);
                 ISS_CUDA_OK(cudaGetLastError());
                 iss_count_launch();
             } else {
@@ -575,21 +503,8 @@ extern "C" int iss_cnn_forward(iss_ctx *ctx, iss_cnn *cnn, const float *d_mspec,
                         f.Cout = d.cout; f.flags = a.flags;
                         const size_t smem = ((size_t)d.kh * d.kw * d.cout + (size_t)f.Hp * f.Wp + FIRST_P * d.sw + d.kw + 8) * sizeof(float);
                         ISS_REQUIRE(smem <= 200 * 1024, ISS_ERR_UNSUPPORTED, "iss_cnn_forward: first layer too large for the direct kernel");
-                        static bool configured = false;
-                        if (!configured) {
-                            ISS_CUDA_OK(cudaFuncSetAttribute(conv_first_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                            configured = true;
-                        }
+                        ISS_CUDA_OK(iss_optin_smem(reinterpret_cast<const void *>(conv_first_direct_kernel), 200 * 1024));
                         const unsigned grid = (unsigned)std::min<int64_t>(nb, (int64_t)ctx->sm_count * 8);
-                        static const bool first_v2 = [] { const char *e = getenv("ISS_B200_FIRST_V2"); return e && e[0] == '1'; }();
-                        if (first_v2 && d.sw == 1 && d.kw <= FIRST_KWMAX) {
-                            static bool configured2 = false;
-                            if (!configured2) {
-                                ISS_CUDA_OK(cudaFuncSetAttribute(conv_first_direct_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                                configured2 = true;
-                            }
-                            conv_first_direct_v2_kernel<<<grid, 256, smem, st>>>(f);
-                        } else
                         conv_first_direct_kernel<<<grid, 256, smem, st>>>(f);
                         ISS_CUDA_OK(cudaGetLastError());
                         iss_count_launch();
@@ -600,7 +515,6 @@ extern "C" int iss_cnn_forward(iss_ctx *ctx, iss_cnn *cnn, const float *d_mspec,
                     }
                 } else {
                     a.in = cur;
-                    if (pool_pending) { a.pool_in = 1; a.inH = pool_in_h; a.inW = pool_in_w; pool_pending = false; }
                     rc = iss_launch_conv(a, false, st);
                 }
                 if (rc != ISS_OK) return rc;

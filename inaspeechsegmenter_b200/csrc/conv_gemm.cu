@@ -194,8 +194,6 @@ int launch_conv_t(const ConvArgs &a, cudaStream_t st)
 
 int iss_launch_conv(const ConvArgs &a, bool first, cudaStream_t st)
 {
-    ISS_REQUIRE(!a.pool_in || (!first && iss_conv_poolin_supported(a, iss_get_gemm_mode())), ISS_ERR_UNSUPPORTED,
-                "iss_launch_conv: fused input pooling requested for a layer that cannot take it");
     if (!first) {
         const int mode = iss_get_gemm_mode();
         if (mode != ISS_GEMM_FP32 && iss_conv_tc_eligible(a)) return iss_launch_conv_tc(a, mode, st);

@@ -313,11 +313,7 @@ int launch_tc3h(const ConvArgs &a, const F16Args &h, int slab_bytes, cudaStream_
 {
     using Cfg = TcHCfg<BN, SB, ST>;
     auto kern = conv_gemm_tc3h_kernel<BN, SB, ST>;
-    static bool configured = false;
-    if (!configured) {
-        ISS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CTA_MAX));
-        configured = true;
-    }
+    ISS_CUDA_OK(iss_optin_smem(reinterpret_cast<const void *>(kern), SMEM_CTA_MAX));
     const int64_t Q = a.M / a.OW;
     const int64_t gm = (Q + a.slab_R - 1) / a.slab_R;
     ISS_REQUIRE(gm < (1ll << 31), ISS_ERR_INVALID, "conv_tc_f16: M too large");
@@ -371,7 +367,6 @@ int iss_launch_conv_tc_f16(ConvArgs &a, cudaStream_t st)
     a.slab_R = R;
     a.slab_rows = rows;
     a.in_elems = a.M / ((int64_t)a.OH * a.OW) * a.H * a.W * a.C;
-    a.prof = nullptr;
     const int BN = a.N % 128 == 0 ? 128 : 64;                   // same n-tiling as iss_prepare_tc_weights
     F16Image im;
     const int rc = get_image(a, BN, &im);

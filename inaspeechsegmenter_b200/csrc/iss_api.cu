@@ -3,6 +3,9 @@
 #include <string.h>
 
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "iss_common.cuh"
 
@@ -20,7 +23,22 @@ static std::atomic<long long> g_launches{0};
 void iss_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 extern "C" int64_t iss_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
 
-extern "C" int iss_version(void) { return 1; }
+cudaError_t iss_optin_smem(const void *func, int bytes)
+{
+    static std::mutex mu;
+    static std::map<std::pair<const void *, int>, int> done;          // (kernel, device) -> bytes opted in
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = done.find({func, dev});
+    if (it != done.end() && it->second >= bytes) return cudaSuccess;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) done[{func, dev}] = bytes;
+    return e;
+}
+
+extern "C" int iss_version(void) { return ISS_ABI_VERSION; }
 
 extern "C" const char *iss_last_error(void) { return g_err; }
 

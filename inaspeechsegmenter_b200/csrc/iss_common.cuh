@@ -9,6 +9,8 @@
 
 void iss_set_error(const char *fmt, ...);
 void iss_count_launch(int n = 1);
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per device: opts `func` in once per (kernel, current device)
+cudaError_t iss_optin_smem(const void *func, int bytes);
 
 #define ISS_CUDA_OK(call)                                                              \
     do {                                                                               \

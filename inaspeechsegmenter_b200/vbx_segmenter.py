@@ -193,17 +193,31 @@ def window_plan(M):
 class B200BackendExtractor(VBxExtractor):
     """ResNet101 x-vector extractor on libiss_b200 (K5)."""
 
-    def __init__(self, state_dict=None, device=0, ctx=None):
+    def __init__(self, state_dict=None, device=0, ctx=None, onnx_path=None):
+        """Weights come from (first match): ``state_dict`` (resnet.py layout), ``onnx_path``, the reference's
+        production asset ``final.onnx`` (vbx_segmenter.py:249-266) or ``raw_81.pth`` (:271-288) in the model
+        directories (models.find_model_file).  The ONNX file is read by onnx_reader (no onnx runtime)."""
         self.ctx = ctx if ctx is not None else Context(device)
+        m, feat_dim, embed_dim, num_blocks = M_CHANNELS, FEAT_DIM, EMBED_DIM, NUM_BLOCKS
         if state_dict is None:
             from .models import find_model_file
-            path = find_model_file('raw_81.pth')
-            if path is None:
-                raise FileNotFoundError('raw_81.pth not found (the reference fetches it from its GitHub release, '
-                                        'remote_utils.py:5,13-14); final.onnx is not readable by this build')
-            state_dict = torch.load(path, map_location='cpu')
-            state_dict = state_dict.get('state_dict', state_dict)
-        blob = np.ascontiguousarray(resnet_blob_from_state(state_dict))
+            onnx_path = onnx_path or find_model_file('final.onnx')
+            if onnx_path is not None:
+                from .onnx_reader import resnet_blob_from_onnx
+                blob, m, feat_dim, embed_dim, num_blocks = resnet_blob_from_onnx(onnx_path)
+                if (m, feat_dim, embed_dim, tuple(num_blocks)) != (M_CHANNELS, FEAT_DIM, EMBED_DIM, NUM_BLOCKS):
+                    raise ValueError('%s is not the VBx ResNet101 (m=%d, feat=%d, embed=%d, blocks=%r)'
+                                     % (onnx_path, m, feat_dim, embed_dim, num_blocks))
+            else:
+                path = find_model_file('raw_81.pth')
+                if path is None:
+                    raise FileNotFoundError('neither final.onnx nor raw_81.pth found (the reference fetches them from its '
+                                            'GitHub release, remote_utils.py:5,13-14; this build does no network access)')
+                state_dict = torch.load(path, map_location='cpu')
+                state_dict = state_dict.get('state_dict', state_dict)
+        if state_dict is not None:
+            blob = resnet_blob_from_state(state_dict)
+        blob = np.ascontiguousarray(blob, dtype=np.float32)
         nb = (ctypes.c_int * 4)(*NUM_BLOCKS)
         lib = _lib.load()
         h = ctypes.c_void_p()

@@ -39,7 +39,8 @@ typedef struct iss_mlp iss_mlp;
 
 /* ---- library / context ------------------------------------------------- */
 
-int         iss_version(void);               /* ABI version, currently 1 */
+#define ISS_ABI_VERSION 2
+int         iss_version(void);               /* == ISS_ABI_VERSION of the header the library was built from */
 const char *iss_last_error(void);
 /* Creates a context bound to CUDA device `device` (one per host thread that
  * issues work).  Fails with ISS_ERR_CUDA if the device is not compute
@@ -50,12 +51,11 @@ int iss_ctx_destroy(iss_ctx *ctx);
  * contexts); bench.py reports the delta over its timed region. */
 int64_t iss_launch_count(void);
 /* GEMM engine used by the conv / dense layers of K2 and K5 (process-wide):
- * 0 = fp32 CUDA cores, 1 = tcgen05 3xTF32 with both operands in shared memory,
- * 2 = tcgen05 3xTF32 with the activation operand in tensor memory (default).  All
- * three are sm_100a code paths of this library with fp32-class accuracy; the default
- * can be overridden with the environment variable ISS_B200_GEMM=fp32|tc_ss|tc_ts.
- * 3 (tc_f16) = EXPERIMENTAL fp16 hi/lo-split variant of 2 for un-padded convolutions
- * (csrc/conv_gemm_tc_f16.cu; not validated on hardware yet, never selected by default). */
+ * 0 = fp32 CUDA cores; 2 = tcgen05 3xTF32 (activation operand in tensor memory) for every
+ * layer shape; 3 (default) = fp16 hi/lo split on tcgen05 kind::f16 for the un-padded stride-1
+ * convolutions of the segmenter CNNs, engine 2 for every other layer.  All are sm_100a code
+ * paths of this library with fp32-class accuracy (<= 1e-5 on the softmax against the fp32
+ * oracle); the default can be overridden with ISS_B200_GEMM=fp32|tc_ts|tc_f16. */
 int iss_set_gemm_mode(int mode);
 int iss_get_gemm_mode(void);
 

@@ -194,9 +194,9 @@ def test_k2_cnn_softmax_vs_oracle(rt, synth_models, which, nmel):
     assert err <= 1e-4, err
 
 
-@pytest.mark.parametrize('mode', [0, 1, 2])
+@pytest.mark.parametrize('mode', [0, 2, 3])
 def test_k2_all_gemm_engines_vs_oracle(rt, synth_models, mode):
-    """fp32 CUDA-core kernel and both tcgen05 3xTF32 variants against the fp32 oracle (1e-4)."""
+    """fp32 CUDA-core kernel, tcgen05 3xTF32 and the default fp16-split tcgen05 engine against the fp32 oracle (1e-4)."""
     from oracle import sidekit_oracle as sk
     lib = rt['lib'].load()
     prev = lib.iss_get_gemm_mode()
@@ -365,7 +365,7 @@ def _alt_keras_cnn(nmel, n_classes, seed):
     return {'class_name': 'Sequential', 'config': {'name': 'alt', 'layers': L}}, W
 
 
-@pytest.mark.parametrize('mode', [0, 2])
+@pytest.mark.parametrize('mode', [0, 2, 3])
 @pytest.mark.parametrize('nmel', [21, 24])
 def test_k2_layer_interpreter_alt_architecture(rt, nmel, mode):
     """The release networks' architecture is unknown here, so the generic layer interpreter is

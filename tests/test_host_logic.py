@@ -35,7 +35,7 @@ def test_abi_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), 'libiss_b200.so does not export %s' % name
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert _lib.load().iss_version() == 1
+    assert _lib.load().iss_version() == _lib.ABI_VERSION
     assert _lib.load().iss_sidekit_num_frames(1192367) == 7450      # musanmix.wav
     assert _lib.load().iss_sidekit_num_frames(399) == 0
 

@@ -141,99 +141,3 @@ def test_bank_conflicts_of_the_two_keys():
     print('extra LDS wavefronts per ideal wavefront: key p&7 = %.3f, row-wrap-free key = %.3f' % (cur, new))
     assert 0.15 < cur < 0.6             # ncu: 43.6 M conflicts / 126 M wavefronts for the whole kernel
     assert new <= 0.25 * cur
-
-
-@pytest.mark.parametrize('W,OW,C,total_px,producers', [(17, 14, 64, 17 * 17, 128), (20, 17, 64, 15 * 20, 128), (7, 5, 64, 29 * 7, 128), (5, 3, 128, 48 * 5, 128), (7, 5, 96, 29 * 7, 256)])
-def test_fill_loop_tracks_row_and_column(W, OW, C, total_px, producers):
-    """The V2 fill keeps (prow, px) of pixel p incrementally (p advances by PRODUCERS / cpp chunks' worth per iteration)."""
-    cpp = C // 4
-    total = total_px * cpp
-    seen = set()
-    for ptid in range(producers):
-        p, j = divmod(ptid, cpp)
-        dp = producers // cpp
-        dj = producers - dp * cpp
-        prow, px = divmod(p, W)
-        q = ptid
-        while q < total:
-            assert (p, j) == divmod(q, cpp) and (prow, px) == divmod(p, W)
-            assert (px + prow * OW) & 7 == key_rowwrap_free(p, W, OW) & 7
-            seen.add(q)
-            p += dp; j += dj; px += dp
-            if j >= cpp:
-                j -= cpp; p += 1; px += 1
-            while px >= W:
-                px -= W; prow += 1
-            q += producers
-    assert len(seen) == total
-
-
-def _emulate_pooled_fill(raw, t, KH, KW, producers=128):
-    """Slab of tile t filled as the POOLIN kernel does: every thread walks its chunks keeping (p, j), (prow, px) and
-    (img, prr) incrementally and stores the 2x2/2 max of the un-pooled tensor `raw` [n_img, inH, inW, C]."""
-    n_img, inH, inW, C = raw.shape
-    H, W = inH // 2, inW // 2
-    OH, OW, R, Q = tile_plan(n_img, H, W, KH, KW)
-    q0 = t * R
-    nq = min(R, Q - q0)
-    img0 = q0 // OH
-    g0 = q0 + img0 * (KH - 1)
-    img1 = (q0 + nq - 1) // OH
-    rows = nq + (KH - 1) * (img1 - img0 + 1)
-    cpp = C // 4
-    total = rows * W * cpp
-    Gtot = n_img * H
-    slab = np.full((total, 4), np.nan, dtype=np.float32)
-    flat = raw.reshape(-1)
-    for ptid in range(producers):
-        p, j = divmod(ptid, cpp)
-        dp, dj = producers // cpp, producers - (producers // cpp) * cpp
-        prow, px = divmod(p, W)
-        img, prr = divmod(g0 + prow, H)
-        q = ptid
-        while q < total:
-            key = px + prow * OW
-            phys = p * cpp + ((j & ~7) | ((j ^ key) & 7))
-            if g0 + prow < Gtot:
-                s0 = ((img * inH + 2 * prr) * inW + 2 * px) * C + j * 4
-                v = np.stack([flat[s0:s0 + 4], flat[s0 + C:s0 + C + 4], flat[s0 + inW * C:s0 + inW * C + 4], flat[s0 + inW * C + C:s0 + inW * C + C + 4]])
-                slab[phys] = v.max(0)
-            else:
-                slab[phys] = 0.0
-            p += dp; j += dj; px += dp
-            if j >= cpp:
-                j -= cpp; p += 1; px += 1
-            while px >= W:
-                px -= W; prow += 1; prr += 1
-                if prr == H:
-                    prr = 0; img += 1
-            q += producers
-    return slab
-
-
-@pytest.mark.parametrize('shape', [(3, 13, 9, 32, 3, 3), (2, 61, 14, 64, 3, 3), (5, 9, 11, 64, 3, 3)])
-def test_pooled_fill_equals_pool_then_fill(shape):
-    """The slab the POOLIN kernel builds == the slab the plain V2 kernel builds from the explicitly pooled tensor."""
-    n_img, inH, inW, C, KH, KW = shape
-    rng = np.random.default_rng(1)
-    raw = rng.standard_normal((n_img, inH, inW, C)).astype(np.float32)
-    H, W = inH // 2, inW // 2
-    pooled = raw[:, :2 * H, :2 * W, :].reshape(n_img, H, 2, W, 2, C).max(axis=(2, 4))
-    OH, OW, R, Q = tile_plan(n_img, H, W, KH, KW)
-    cpp = C // 4
-    for t in range((Q + R - 1) // R):
-        got = _emulate_pooled_fill(raw, t, KH, KW)
-        # reference slab: contiguous rows of the pooled tensor, swizzled with the V2 key (zero past the end)
-        q0 = t * R
-        nq = min(R, Q - q0)
-        img0 = q0 // OH
-        g0 = q0 + img0 * (KH - 1)
-        rows = nq + (KH - 1) * ((q0 + nq - 1) // OH - img0 + 1)
-        flat = pooled.reshape(-1)
-        want = np.zeros_like(got)
-        for q in range(rows * W * cpp):
-            p, j = divmod(q, cpp)
-            phys = p * cpp + ((j & ~7) | ((j ^ key_rowwrap_free(p, W, OW)) & 7))
-            src = g0 * W * C + q * 4
-            want[phys] = flat[src:src + 4] if src + 4 <= flat.size else 0.0
-        assert np.array_equal(got, want)

@@ -108,10 +108,10 @@ def test_k5_resnet_vs_oracle(vctx, golden):
     lib = _lib_mod().load()
     prev = lib.iss_get_gemm_mode()
     # tolerance relative to max|y| after 104 convolution layers: fp32 CUDA-core engine 2e-5;
-    # tcgen05 3xTF32 engines 2e-4 (tensor-core accumulation truncates; measured 7.5e-5).  The
+    # tcgen05 engines 1e-4 (tensor-core accumulation truncates; measured 7.5e-5).  The
     # reference's own check of this network is 4 decimals (run_test.py:189-195).
     try:
-        for mode, tol in ((0, 2e-5), (1, 2e-4), (2, 2e-4)):
+        for mode, tol in ((0, 2e-5), (2, 1e-4), (3, 1e-4)):
             lib.iss_set_gemm_mode(mode)
             for i in range(len(x)):
                 got = ext.get_embedding(x[i].T)                    # get_embedding takes [T, 64]

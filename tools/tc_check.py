@@ -2,8 +2,8 @@
 """Bring-up check of the tcgen05 GEMM modes: run the VAD stand-in CNN on synthetic
 log-mel with one GEMM mode, compare with the fp32 CUDA-core result saved by mode 0,
 and time a larger batch.  Each mode runs in its own process (a hung kernel must not
-take the others down):  python tools/tc_check.py <mode 0|1|2|3> [minutes]
-(3 = the experimental fp16-split engine; run mode 0 first so the reference file exists)."""
+take the others down):  python tools/tc_check.py <mode 0|2|3> [minutes]
+(3 = the default fp16-split engine; run mode 0 first so the reference file exists)."""
 import os
 import sys
 import time
