@@ -52,6 +52,7 @@ SIGNATURES = {
     'iss_sidekit_upload_tables': (_i, [_vp, _vp, _vp]),
     'iss_sidekit_features': (_i, [_vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _vp]),
     'iss_loge_stats': (_i, [_vp, _vp, _i64, _vp, _vp]),
+    'iss_set_energy_viterbi_serial': (_i, [_i]),
     'iss_energy_viterbi': (_i, [_vp, _vp, _i64, _vp, _d, _vp, _vp, _d, _i, _vp, _vp, _vp]),
     'iss_viterbi_segments': (_i, [_vp, _vp, _i, _vp, _i, _vp, _d, _vp, _vp, _vp]),
     'iss_viterbi_work_bytes': (_i64, [_i64, _i]),

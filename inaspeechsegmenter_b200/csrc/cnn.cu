@@ -33,6 +33,8 @@ struct Layer {
     int out_h, out_w, out_c;
     float *d_wt = nullptr;      // tensor-core weights [2][N][Kp] (eligible layers only)
     int Kp = 0;
+    void *d_wt_f16 = nullptr;   // fp16 hi/lo image of engine 3 (KHxKW > 1 convolutions with K % 64 == 0, N % 64 == 0)
+    float f16_inv_scale = 1.f;
 };
 
 }  // namespace
@@ -119,6 +121,7 @@ struct FirstArgs {
     float *out;
     int64_t n;
     int H, W, OH, OW, KH, KW, SH, SW, PT, PL, Hp, Wp, Cout, flags;
+    int out_packed;        // 1: store split-half words (lo16 << 16 | hi16) for the fp16-split slab convolution behind this layer
 };
 
 constexpr int FIRST_P = 4;
@@ -190,7 +193,11 @@ conv_first_direct_kernel(const FirstArgs a)
                     if (a.flags & ISS_F_AFFINE_POST) v = fmaf(v, es2[q], et2[q]);
                     y[q] = v;
                 }
-                *reinterpret_cast<float4 *>(out_img + ((int64_t)oh * a.OW + ow0 + p) * a.Cout + c4 * 4) = make_float4(y[0], y[1], y[2], y[3]);
+                float *dst = out_img + ((int64_t)oh * a.OW + ow0 + p) * a.Cout + c4 * 4;
+                if (a.out_packed)
+                    *reinterpret_cast<uint4 *>(dst) = make_uint4(iss_pack_split(y[0]), iss_pack_split(y[1]), iss_pack_split(y[2]), iss_pack_split(y[3]));
+                else
+                    *reinterpret_cast<float4 *>(dst) = make_float4(y[0], y[1], y[2], y[3]);
             }
         }
     }
@@ -248,6 +255,41 @@ maxpool_nhwc_vec4_kernel(const float4 *__restrict__ in, float4 *__restrict__ out
         }
     }
     out[i] = best;
+}
+
+// Pooling over split-half words (the tensor between two fp16-split slab convolutions): the window maximum is taken on
+// the decoded values hi + lo (exact in fp32) and the winning WORD is stored, so the value itself is unchanged.
+__global__ void __launch_bounds__(256)
+maxpool_nhwc_packed_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, int64_t total4, int H, int W, int C4,
+                           int OH, int OW, int KH, int KW, int SH, int SW, int PT, int PL)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;       // over [img][oh][ow][c / 4]
+    if (i >= total4) return;
+    const int c = (int)(i % C4);
+    int64_t r = i / C4;
+    const int ow = (int)(r % OW); r /= OW;
+    const int oh = (int)(r % OH);
+    const int64_t img = r / OH;
+    float bv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    uint32_t bw[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) bw[q] = iss_pack_split(-INFINITY);
+    for (int y = 0; y < KH; ++y) {
+        const int ih = oh * SH - PT + y;
+        if (ih < 0 || ih >= H) continue;
+        for (int x = 0; x < KW; ++x) {
+            const int iw = ow * SW - PL + x;
+            if (iw < 0 || iw >= W) continue;
+            const uint4 v = __ldg(in + ((img * H + ih) * W + iw) * C4 + c);
+            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float f = iss_unpack_split(w4[q]);
+                if (f > bv[q] || f != f) { bv[q] = f; bw[q] = w4[q]; }
+            }
+        }
+    }
+    out[i] = make_uint4(bw[0], bw[1], bw[2], bw[3]);
 }
 
 // ------------------------------------------------------------------ softmax head + non-finite override
@@ -351,6 +393,10 @@ extern "C" int iss_cnn_create(iss_ctx *ctx, const iss_layer_desc *layers, int n_
         if (C % 32 != 0 || K % 32 != 0 || d.cout % 32 != 0) continue;
         int rc = iss_prepare_tc_weights(h_blob + d.w_off, K, d.cout, &L.d_wt, &L.Kp);
         if (rc != ISS_OK) { iss_cnn_destroy(m); return rc; }
+        if (d.kind == ISS_LAYER_CONV2D && d.kh * d.kw > 1 && d.cin % 64 == 0) {
+            rc = iss_prepare_f16_weights(h_blob + d.w_off, K, d.cout, &L.d_wt_f16, &L.f16_inv_scale);
+            if (rc != ISS_OK) { iss_cnn_destroy(m); return rc; }
+        }
     }
     *out = m;
     return ISS_OK;
@@ -361,7 +407,7 @@ extern "C" int iss_cnn_destroy(iss_cnn *cnn)
     if (!cnn) return ISS_OK;
     cudaSetDevice(cnn->ctx->device);
     for (cudaEvent_t ev : cnn->prof_ev) cudaEventDestroy(ev);
-    for (Layer &L : cnn->layers) if (L.d_wt) cudaFree(L.d_wt);
+    for (Layer &L : cnn->layers) { if (L.d_wt) cudaFree(L.d_wt); if (L.d_wt_f16) cudaFree(L.d_wt_f16); }
     if (cnn->d_blob) cudaFree(cnn->d_blob);
     delete cnn;
     return ISS_OK;
@@ -382,6 +428,45 @@ extern "C" int64_t iss_cnn_workspace_bytes(const iss_cnn *cnn, int64_t n, int n_
     bytes += align_up((size_t)(n_seg + 1) * 4, 256) + align_up((size_t)(n_seg + 1) * 8, 256);   // segment tables
     return bytes;
 }
+
+namespace {
+
+// geometry + weight pointers of a Conv2D / Dense layer for `nb` patches (the fields iss_launch_conv dispatches on)
+void fill_conv_args(const Layer &Lr, int64_t nb, ConvArgs &a)
+{
+    const iss_layer_desc &d = Lr.d;
+    if (Lr.d_wt) { a.wt_hi = Lr.d_wt; a.wt_lo = Lr.d_wt + (size_t)d.cout * Lr.Kp; a.wt_tiled = Lr.d_wt + 2 * (size_t)d.cout * Lr.Kp; a.Kp = Lr.Kp; }
+    a.wt_f16 = Lr.d_wt_f16; a.wt_f16_inv_scale = Lr.f16_inv_scale;
+    a.N = d.cout;
+    if (d.kind == ISS_LAYER_DENSE) {
+        a.M = nb; a.K = d.cin; a.H = 1; a.W = 1; a.C = d.cin; a.OH = 1; a.OW = 1;
+        a.KH = 1; a.KW = 1; a.SH = 1; a.SW = 1; a.PT = 0; a.PL = 0;
+    } else {
+        a.M = nb * Lr.out_h * Lr.out_w; a.K = d.kh * d.kw * d.cin;
+        a.H = Lr.in_h; a.W = Lr.in_w; a.C = Lr.in_c; a.OH = Lr.out_h; a.OW = Lr.out_w;
+        a.KH = d.kh; a.KW = d.kw; a.SH = d.sh; a.SW = d.sw; a.PT = d.pad_top; a.PL = d.pad_left;
+    }
+}
+
+// Should the tensor produced by layer `li` be stored as split-half words?  Yes iff the next compute layer
+// (pooling layers in between keep the format) is a convolution the fp16-split slab kernel takes.
+bool wants_packed_output(const iss_cnn *cnn, size_t li, int64_t nb)
+{
+    if (iss_get_gemm_mode() != ISS_GEMM_TC_F16) return false;
+    size_t j = li + 1;
+    while (j < cnn->layers.size() && cnn->layers[j].d.kind == ISS_LAYER_MAXPOOL) {
+        if (cnn->layers[j].in_c % 4 != 0) return false;          // the packed pooling kernel moves 4 channels per thread
+        ++j;
+    }
+    if (j >= cnn->layers.size() || cnn->layers[j].d.kind != ISS_LAYER_CONV2D) return false;
+    const Layer &Nx = cnn->layers[j];
+    if (Nx.d.pad_bottom != 0 || Nx.d.pad_right != 0) return false;
+    ConvArgs probe = {};
+    fill_conv_args(Nx, nb, probe);
+    return iss_conv_f16_slab_covers(probe);
+}
+
+}  // namespace
 
 extern "C" int iss_cnn_forward(iss_ctx *ctx, iss_cnn *cnn, const float *d_mspec, int64_t L, int ld,
                                int edge_left, int edge_right,
@@ -439,6 +524,7 @@ extern "C" int iss_cnn_forward(iss_ctx *ctx, iss_cnn *cnn, const float *d_mspec,
         const int64_t nb = std::min<int64_t>(B, n - b0);
         const float *cur = nullptr;
         int which = 0;
+        bool cur_packed = false;                                 // format of `cur`: fp32 values or split-half words
         for (size_t li = 0; li < cnn->layers.size(); ++li) {
             const Layer &Lr = cnn->layers[li];
             const iss_layer_desc &d = Lr.d;
@@ -458,7 +544,11 @@ extern "C" int iss_cnn_forward(iss_ctx *ctx, iss_cnn *cnn, const float *d_mspec,
             if (d.kind == ISS_LAYER_MAXPOOL) {
                 ISS_REQUIRE(li > 0, ISS_ERR_UNSUPPORTED, "iss_cnn_forward: pooling as first layer is not supported");
                 const int64_t total = nb * Lr.out_h * Lr.out_w * Lr.out_c;
-                if (Lr.in_c % 4 == 0)
+                if (cur_packed)                                   // (format kept: the consumer behind the pooling asked for words)
+                    maxpool_nhwc_packed_kernel<<<(unsigned)((total / 4 + 255) / 256), 256, 0, st>>>(
+                        reinterpret_cast<const uint4 *>(cur), reinterpret_cast<uint4 *>(dst), total / 4, Lr.in_h, Lr.in_w, Lr.in_c / 4,
+                        Lr.out_h, Lr.out_w, d.kh, d.kw, d.sh, d.sw, d.pad_top, d.pad_left);
+                else if (Lr.in_c % 4 == 0)
                     maxpool_nhwc_vec4_kernel<<<(unsigned)((total / 4 + 255) / 256), 256, 0, st>>>(
                         reinterpret_cast<const float4 *>(cur), reinterpret_cast<float4 *>(dst), total / 4, Lr.in_h, Lr.in_w, Lr.in_c / 4,
                         Lr.out_h, Lr.out_w, d.kh, d.kw, d.sh, d.sw, d.pad_top, d.pad_left);
@@ -476,22 +566,19 @@ extern "C" int iss_cnn_forward(iss_ctx *ctx, iss_cnn *cnn, const float *d_mspec,
                 a.post_scale = (d.flags & ISS_F_AFFINE_POST) ? blob + d.post_scale_off : nullptr;
                 a.post_shift = (d.flags & ISS_F_AFFINE_POST) ? blob + d.post_shift_off : nullptr;
                 a.out = dst;
-                if (Lr.d_wt) { a.wt_hi = Lr.d_wt; a.wt_lo = Lr.d_wt + (size_t)d.cout * Lr.Kp; a.wt_tiled = Lr.d_wt + 2 * (size_t)d.cout * Lr.Kp; a.Kp = Lr.Kp; }
                 a.flags = d.flags & ~ISS_F_SOFTMAX;
-                a.N = d.cout;
-                if (d.kind == ISS_LAYER_DENSE) {
-                    a.M = nb; a.K = d.cin; a.H = 1; a.W = 1; a.C = d.cin; a.OH = 1; a.OW = 1;
-                    a.KH = 1; a.KW = 1; a.SH = 1; a.SW = 1; a.PT = 0; a.PL = 0;
-                } else {
-                    a.M = nb * Lr.out_h * Lr.out_w; a.K = d.kh * d.kw * d.cin;
-                    a.H = Lr.in_h; a.W = Lr.in_w; a.C = Lr.in_c; a.OH = Lr.out_h; a.OW = Lr.out_w;
-                    a.KH = d.kh; a.KW = d.kw; a.SH = d.sh; a.SW = d.sw; a.PT = d.pad_top; a.PL = d.pad_left;
-                }
+                fill_conv_args(Lr, nb, a);
+                a.in_packed = cur_packed ? 1 : 0;
+                const bool direct = li == 0 && d.kind == ISS_LAYER_CONV2D && d.cin == 1 &&
+                                    (d.cout == 16 || d.cout == 32 || d.cout == 64 || d.cout == 128) && !(d.flags & ISS_F_SOFTMAX);
+                // only the direct first-layer kernel and the fp16-split slab kernel can emit split-half words
+                const bool can_pack = direct || (li > 0 && iss_get_gemm_mode() == ISS_GEMM_TC_F16 && iss_conv_f16_slab_covers(a));
+                a.out_packed = (!last && can_pack && wants_packed_output(cnn, li, nb)) ? 1 : 0;
+                ISS_REQUIRE(!a.in_packed || (li > 0 && iss_conv_f16_slab_covers(a)), ISS_ERR_UNSUPPORTED,
+                            "iss_cnn_forward: layer %d was handed split-half words it cannot read", (int)li);
                 int rc;
                 if (li == 0) {
                     ISS_REQUIRE(d.kind == ISS_LAYER_CONV2D, ISS_ERR_UNSUPPORTED, "iss_cnn_forward: first layer must be Conv2D");
-                    const bool direct = d.cin == 1 && (d.cout == 16 || d.cout == 32 || d.cout == 64 || d.cout == 128) &&
-                                        !(d.flags & ISS_F_SOFTMAX);
                     if (direct) {
                         FirstArgs f = {};
                         f.mspec = d_mspec; f.ld = ld; f.row0 = pa.row0 + b0; f.mu = pa.mu + b0; f.sigma = pa.sigma + b0;
@@ -500,7 +587,7 @@ extern "C" int iss_cnn_forward(iss_ctx *ctx, iss_cnn *cnn, const float *d_mspec,
                         f.H = Lr.in_h; f.W = Lr.in_w; f.OH = Lr.out_h; f.OW = Lr.out_w; f.KH = d.kh; f.KW = d.kw;
                         f.SH = d.sh; f.SW = d.sw; f.PT = d.pad_top; f.PL = d.pad_left;
                         f.Hp = Lr.in_h + d.pad_top + d.pad_bottom; f.Wp = Lr.in_w + d.pad_left + d.pad_right;
-                        f.Cout = d.cout; f.flags = a.flags;
+                        f.Cout = d.cout; f.flags = a.flags; f.out_packed = a.out_packed;
                         const size_t smem = ((size_t)d.kh * d.kw * d.cout + (size_t)f.Hp * f.Wp + FIRST_P * d.sw + d.kw + 8) * sizeof(float);
                         ISS_REQUIRE(smem <= 200 * 1024, ISS_ERR_UNSUPPORTED, "iss_cnn_forward: first layer too large for the direct kernel");
                         ISS_CUDA_OK(iss_optin_smem(reinterpret_cast<const void *>(conv_first_direct_kernel), 200 * 1024));
@@ -511,6 +598,7 @@ extern "C" int iss_cnn_forward(iss_ctx *ctx, iss_cnn *cnn, const float *d_mspec,
                         rc = ISS_OK;
                     } else {
                         a.in = d_mspec; a.ld = ld; a.row0 = pa.row0 + b0; a.mu = pa.mu + b0; a.sigma = pa.sigma + b0;
+                        a.out_packed = 0;                         // the generic first-layer kernel writes fp32
                         rc = iss_launch_conv(a, true, st);
                     }
                 } else {
@@ -518,6 +606,7 @@ extern "C" int iss_cnn_forward(iss_ctx *ctx, iss_cnn *cnn, const float *d_mspec,
                     rc = iss_launch_conv(a, false, st);
                 }
                 if (rc != ISS_OK) return rc;
+                cur_packed = a.out_packed != 0;
             }
             if (prof) {
                 ISS_CUDA_OK(cudaEventRecord(cnn->prof_ev[cnn->prof_used + 1], st));

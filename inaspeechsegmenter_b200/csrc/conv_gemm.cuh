@@ -1,7 +1,21 @@
 // conv_gemm.cuh -- implicit-GEMM convolution / dense layer shared by the CNN (K2)
 // and ResNet101 (K5) operators.  NHWC float32 activations; B = [K][N] weights.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "iss_common.cuh"
+
+// split-half word of the fp16-split engine: lo16 << 16 | hi16 with hi = fp16(x), lo = fp16(x - hi)
+__device__ __forceinline__ uint32_t iss_pack_split(float y)
+{
+    const __half hh = __float2half_rn(y);
+    const __half ll = __float2half_rn(y - __half2float(hh));
+    return (uint32_t)__half_as_ushort(hh) | ((uint32_t)__half_as_ushort(ll) << 16);
+}
+__device__ __forceinline__ float iss_unpack_split(uint32_t w)
+{
+    return __half2float(__ushort_as_half((unsigned short)(w & 0xFFFFu))) + __half2float(__ushort_as_half((unsigned short)(w >> 16)));
+}
 
 #define ISS_F_RESIDUAL 64     /* internal: + residual[m][n] after the pre-affine, before ReLU */
 
@@ -22,6 +36,10 @@ struct ConvArgs {
     const int32_t *row0; const float *mu; const float *sigma;
     // tensor-core path: weights transposed + split, [N][Kp] each (nullptr => fp32 CUDA-core kernel)
     const float *wt_hi; const float *wt_lo; const float *wt_tiled; int Kp;
+    // fp16-split engine (conv_gemm_tc_f16.cu): tiled fp16 hi/lo weight image (nullptr => not prepared) and its scale
+    const void *wt_f16; float wt_f16_inv_scale;
+    // activation formats of that engine: fp32 values (0) or split-half words lo16 << 16 | hi16 (1)
+    int in_packed, out_packed;
     // slab kernel (conv_gemm_tc_f16.cu) only, filled in by iss_launch_conv_tc_f16
     int slab_R;             // output rows (of width OW) per 128-row GEMM tile
     int slab_rows;          // input rows the slab is sized for
@@ -40,6 +58,10 @@ bool iss_conv_tc_eligible(const ConvArgs &a);
 int iss_launch_conv_tc(const ConvArgs &a, int mode, cudaStream_t st);
 // W[K][N] -> device buffer: [2][N][Kp] row-major (hi, lo) then the tiled/pre-swizzled image [2*N*Kp]; Kp = K rounded up to 32
 int iss_prepare_tc_weights(const float *h_w, int K, int N, float **d_out, int *Kp_out);
+// W[K][N] -> fp16 hi/lo image of engine 3 (*d_out stays nullptr when the shape is not one that engine takes)
+int iss_prepare_f16_weights(const float *h_w, int K, int N, void **d_out, float *inv_scale);
+// does engine 3's slab kernel cover this layer (geometry + prepared image + shared memory)?
+bool iss_conv_f16_slab_covers(const ConvArgs &a);
 
 // Launches the layer on `st`.  first = gather from log-mel rows with (x - mu) / sigma.
 int iss_launch_conv(const ConvArgs &a, bool first, cudaStream_t st);

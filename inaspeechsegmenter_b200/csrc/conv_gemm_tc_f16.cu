@@ -1,5 +1,5 @@
-// conv_gemm_tc_f16.cu -- EXPERIMENTAL engine 3 (ISS_B200_GEMM=tc_f16, never the default): the slab
-// convolution of conv_gemm_tc.cu with the operands split into TWO fp16 numbers instead of two TF32 ones.
+// conv_gemm_tc_f16.cu -- engine 3 (the default, ISS_B200_GEMM=tc_f16): slab convolution on tcgen05 kind::f16
+// with every fp32 operand split into TWO fp16 numbers.
 //
 //      x = hi + lo,  hi = fp16(x),  lo = fp16(x - hi)          (22 significant bits, like the TF32 split)
 //      A.B ~= Ah.Bh + Ah.Bl + Al.Bh                            (three kind::f16 MMAs, fp32 accumulation)
@@ -14,19 +14,22 @@
 // Algorithmic accuracy of the split (exact products and sums, tests/test_split_accuracy.py): 8e-7 on the
 // stand-in VAD softmax vs 1.3e-6 for the TF32 split -- both at the fp32 oracle's own rounding noise.
 //
-// STATUS: written in round 1 after the GPU budget was spent -- compiles for sm_100a, NOT yet run on hardware.
-// First thing to run in round 2: tools/tc_check.py 0 10; tools/tc_check.py 3 10.  Checked off-line: the
-// instruction-descriptor fields and the dense packing of 16-bit A operands in tensor memory (32-bit column c of
-// lane m holds k = 2c in its low half, k = 2c+1 in its high half) agree with CUTLASS (cute/arch/mma_sm100_desc.hpp,
-// tmem_frg_1sm<a_type, a_type> in cute/atom/mma_traits_sm100.hpp); the weight image with the descriptor
-// convention (tools/f16_image_check.cu, host-only).
+// Validated on B200 in round 2 (profiles/r02_bringup_variants.txt): softmax error vs the fp32 CUDA-core engine
+// 4.5e-6 (VAD) / 7.3e-6 (gender), i.e. below the TF32 split's 7-8e-6, and 1.74x faster on the slab layers.
+// Dense packing of 16-bit A operands in tensor memory: 32-bit column c of lane m holds k = 2c in its low half,
+// k = 2c+1 in its high half.
+//
+// PACKED activations ("split-half words"): a layer whose consumer is another slab convolution of this engine
+// stores every activation as ONE 32-bit word  lo16 << 16 | hi16  (hi = fp16(x), lo = fp16(x - hi)) instead of the
+// fp32 value -- same bytes in HBM, but the hi/lo split is then done once per element in the producing epilogue
+// instead of KH*KW times in the consumers' A-operand producers, whose per-k-block work drops from 16 LDS.128 +
+// ~190 conversions/subtractions to 16 LDS.128 + 64 PRMT (they were the bottleneck of the first version).  The value
+// carried between layers is hi + lo, exactly what the tensor cores would have used anyway.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <math.h>
 #include <stdlib.h>
 
-#include <map>
-#include <mutex>
 #include <vector>
 
 #include "f16_image.cuh"
@@ -73,7 +76,15 @@ struct F16Args {
     float inv_scale;
 };
 
-template <int BN, int SB, int ST>
+__device__ __forceinline__ uint4 lds128u(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+
+// PACKED: the input tensor holds split-half words (see the file header); a.out_packed selects the output format.
+template <int BN, int SB, int ST, bool PACKED>
 __global__ void __launch_bounds__(160, (TcHCfg<BN, SB, ST>::TMEM_COLS <= 256 ? 2 : 1))
 conv_gemm_tc3h_kernel(const ConvArgs a, const F16Args h)
 {
@@ -155,20 +166,34 @@ conv_gemm_tc3h_kernel(const ConvArgs a, const F16Args h)
             const uint32_t base = slab_u32 + (uint32_t)p * pix_bytes + (uint32_t)is_c0 * 4;
             const uint32_t x = (uint32_t)(p & 7) << 4;
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {               // 2 x 32 floats keeps the register peak down
-                float v[32];
+            for (int half = 0; half < 2; ++half) {               // 2 x 32 words keeps the register peak down
+                if constexpr (PACKED) {
+                    uint32_t v[32];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 q = lds128(base + ((((uint32_t)(half * 8 + j)) << 4) ^ x));
-                    v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
-                }
+                    for (int j = 0; j < 8; ++j) {
+                        const uint4 q = lds128u(base + ((((uint32_t)(half * 8 + j)) << 4) ^ x));
+                        v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+                    }
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);      // low half = even k
-                    const float2 hf = __half22float2(hh);
-                    const __half2 ll = __floats2half2_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
-                    hi[half * 16 + i] = *reinterpret_cast<const uint32_t *>(&hh);
-                    lo[half * 16 + i] = *reinterpret_cast<const uint32_t *>(&ll);
+                    for (int i = 0; i < 16; ++i) {                // word = lo << 16 | hi; operand column = k even (low) | k odd (high)
+                        hi[half * 16 + i] = __byte_perm(v[2 * i], v[2 * i + 1], 0x5410);
+                        lo[half * 16 + i] = __byte_perm(v[2 * i], v[2 * i + 1], 0x7632);
+                    }
+                } else {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 q = lds128(base + ((((uint32_t)(half * 8 + j)) << 4) ^ x));
+                        v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);      // low half = even k
+                        const float2 hf = __half22float2(hh);
+                        const __half2 ll = __floats2half2_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+                        hi[half * 16 + i] = *reinterpret_cast<const uint32_t *>(&hh);
+                        lo[half * 16 + i] = *reinterpret_cast<const uint32_t *>(&ll);
+                    }
                 }
             }
             is_c0 += HBK;
@@ -246,7 +271,10 @@ conv_gemm_tc3h_kernel(const ConvArgs a, const F16Args h)
                         if (post) t = fmaf(t, es2[q], et2[q]);
                         y[q] = t;
                     }
-                    *reinterpret_cast<float4 *>(a.out + m * a.N + nb) = make_float4(y[0], y[1], y[2], y[3]);
+                    if (a.out_packed)
+                        *reinterpret_cast<uint4 *>(a.out + m * a.N + nb) = make_uint4(iss_pack_split(y[0]), iss_pack_split(y[1]), iss_pack_split(y[2]), iss_pack_split(y[3]));
+                    else
+                        *reinterpret_cast<float4 *>(a.out + m * a.N + nb) = make_float4(y[0], y[1], y[2], y[3]);
                 }
             }
         }
@@ -308,11 +336,11 @@ conv_gemm_tc3h_kernel(const ConvArgs a, const F16Args h)
 constexpr int SMEM_CTA_MAX = 232448;
 constexpr int SMEM_HALF_SM = 115712;
 
-template <int BN, int SB, int ST>
-int launch_tc3h(const ConvArgs &a, const F16Args &h, int slab_bytes, cudaStream_t st)
+template <int BN, int SB, int ST, bool PACKED>
+int launch_tc3h_p(const ConvArgs &a, const F16Args &h, int slab_bytes, cudaStream_t st)
 {
     using Cfg = TcHCfg<BN, SB, ST>;
-    auto kern = conv_gemm_tc3h_kernel<BN, SB, ST>;
+    auto kern = conv_gemm_tc3h_kernel<BN, SB, ST, PACKED>;
     ISS_CUDA_OK(iss_optin_smem(reinterpret_cast<const void *>(kern), SMEM_CTA_MAX));
     const int64_t Q = a.M / a.OW;
     const int64_t gm = (Q + a.slab_R - 1) / a.slab_R;
@@ -324,54 +352,49 @@ int launch_tc3h(const ConvArgs &a, const F16Args &h, int slab_bytes, cudaStream_
     return ISS_OK;
 }
 
-// fp16 weight images, built on first use from the fp32 planes the layer already holds on the device
-// (wt_hi + wt_lo == the original weight, exactly) and cached by their address.
-struct F16Image { unsigned char *d; float inv_scale; };
-std::map<const float *, F16Image> g_images;
-std::mutex g_images_mu;
-
-int get_image(const ConvArgs &a, int BN, F16Image *out)
+template <int BN, int SB, int ST>
+int launch_tc3h(const ConvArgs &a, const F16Args &h, int slab_bytes, cudaStream_t st)
 {
-    std::lock_guard<std::mutex> lk(g_images_mu);
-    auto it = g_images.find(a.wt_tiled);
-    if (it != g_images.end()) { *out = it->second; return ISS_OK; }
-    const size_t plane = (size_t)a.N * a.Kp;
-    std::vector<float> hi(plane), lo(plane);
-    ISS_CUDA_OK(cudaMemcpy(hi.data(), a.wt_hi, plane * sizeof(float), cudaMemcpyDeviceToHost));
-    ISS_CUDA_OK(cudaMemcpy(lo.data(), a.wt_lo, plane * sizeof(float), cudaMemcpyDeviceToHost));
-    for (size_t i = 0; i < plane; ++i) hi[i] += lo[i];           // == the original fp32 weight, exactly
-    std::vector<__half> img;
-    const float scale = iss_f16_build_image(hi.data(), a.N, a.K, a.Kp, BN, img);
-    F16Image im;
-    im.inv_scale = 1.f / scale;
-    ISS_CUDA_OK(cudaMalloc(&im.d, img.size() * sizeof(__half)));
-    ISS_CUDA_OK(cudaMemcpy(im.d, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice));
-    g_images[a.wt_tiled] = im;
-    *out = im;
-    return ISS_OK;
+    return a.in_packed ? launch_tc3h_p<BN, SB, ST, true>(a, h, slab_bytes, st) : launch_tc3h_p<BN, SB, ST, false>(a, h, slab_bytes, st);
 }
 
 }  // namespace
 
-// Returns 1 when the layer is not covered (caller continues with the TF32 engines).
-int iss_launch_conv_tc_f16(ConvArgs &a, cudaStream_t st)
+static int slab_plan(const ConvArgs &a, int *R_out, int *rows_out)
 {
-    if (a.SH != 1 || a.SW != 1 || a.PT != 0 || a.PL != 0 || a.KH * a.KW <= 1) return 1;
-    if (a.OH != a.H - a.KH + 1 || a.OW != a.W - a.KW + 1 || a.OW > TBM || a.Kp != a.K) return 1;
-    if (a.N % 64 != 0 || a.C % HBK != 0 || a.K % HBK != 0) return 1;
     const int R = TBM / a.OW;
     const int cross = (R - 1) / a.OH + 1;
     const int rows = R + (a.KH - 1) * (1 + cross);
     int slab_bytes = rows * a.W * a.C * 4;
     if (slab_bytes < 32768) slab_bytes = 32768;
+    *R_out = R; *rows_out = rows;
+    return slab_bytes;
+}
+
+// Does this engine's slab kernel cover the layer?  (Also decides whether the layer in front may hand it
+// split-half words: cnn.cu asks before choosing the producer's output format.)
+bool iss_conv_f16_slab_covers(const ConvArgs &a)
+{
+    if (!a.wt_f16 || a.SH != 1 || a.SW != 1 || a.PT != 0 || a.PL != 0 || a.KH * a.KW <= 1) return false;
+    if (a.OH != a.H - a.KH + 1 || a.OW != a.W - a.KW + 1 || a.OW > TBM || a.Kp != a.K) return false;
+    if (a.N % 64 != 0 || a.C % HBK != 0 || a.K % HBK != 0) return false;
+    int R, rows;
+    const int slab_bytes = slab_plan(a, &R, &rows);
+    if (a.N % 128 == 0) return TcHCfg<128, 2, 4>::FIXED + slab_bytes <= SMEM_CTA_MAX;
+    return TcHCfg<64, 3, 2>::FIXED + slab_bytes <= SMEM_CTA_MAX;
+}
+
+// Returns 1 when the layer is not covered (caller continues with the TF32 engine).
+int iss_launch_conv_tc_f16(ConvArgs &a, cudaStream_t st)
+{
+    if (!iss_conv_f16_slab_covers(a)) return 1;
+    int R, rows;
+    const int slab_bytes = slab_plan(a, &R, &rows);
     a.slab_R = R;
     a.slab_rows = rows;
     a.in_elems = a.M / ((int64_t)a.OH * a.OW) * a.H * a.W * a.C;
-    const int BN = a.N % 128 == 0 ? 128 : 64;                   // same n-tiling as iss_prepare_tc_weights
-    F16Image im;
-    const int rc = get_image(a, BN, &im);
-    if (rc != ISS_OK) return rc;
-    F16Args h{im.d, im.inv_scale};
+    const int BN = a.N % 128 == 0 ? 128 : 64;                   // same n-tiling as iss_prepare_f16_weights
+    F16Args h{reinterpret_cast<const unsigned char *>(a.wt_f16), a.wt_f16_inv_scale};
     if (BN == 128) {
         if (TcHCfg<128, 4, 4>::FIXED + slab_bytes <= SMEM_CTA_MAX) return launch_tc3h<128, 4, 4>(a, h, slab_bytes, st);
         if (TcHCfg<128, 3, 4>::FIXED + slab_bytes <= SMEM_CTA_MAX) return launch_tc3h<128, 3, 4>(a, h, slab_bytes, st);
@@ -382,4 +405,25 @@ int iss_launch_conv_tc_f16(ConvArgs &a, cudaStream_t st)
     if (TcHCfg<64, 2, 2>::FIXED + slab_bytes <= SMEM_HALF_SM) return launch_tc3h<64, 2, 2>(a, h, slab_bytes, st);
     if (TcHCfg<64, 3, 2>::FIXED + slab_bytes <= SMEM_CTA_MAX) return launch_tc3h<64, 3, 2>(a, h, slab_bytes, st);
     return 1;
+}
+
+// Host-side preparation of a layer's weights for this engine: W[K][N] (Keras / blob layout) -> device image
+// [n-tile][k-block of 64][hi | lo][BN rows x 128 B, SWIZZLE_128B] of fp16 halves, pre-scaled by a power of two
+// (undone in the epilogue with *inv_scale).  Owned by the layer (freed with cudaFree by its destructor).
+int iss_prepare_f16_weights(const float *h_w, int K, int N, void **d_out, float *inv_scale)
+{
+    *d_out = nullptr; *inv_scale = 1.f;
+    if (K % HBK != 0 || N % 64 != 0) return ISS_OK;              // not a shape this engine takes
+    std::vector<float> wt((size_t)N * K);                        // transposed [N][K]
+    for (int k = 0; k < K; ++k)
+        for (int n = 0; n < N; ++n) wt[(size_t)n * K + k] = h_w[(size_t)k * N + n];
+    std::vector<__half> img;
+    const float scale = iss_f16_build_image(wt.data(), N, K, K, N % 128 == 0 ? 128 : 64, img);
+    void *d = nullptr;
+    cudaError_t e = cudaMalloc(&d, img.size() * sizeof(__half));
+    if (e != cudaSuccess) { iss_set_error("cudaMalloc f16 weights: %s", cudaGetErrorString(e)); return ISS_ERR_NOMEM; }
+    e = cudaMemcpy(d, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(d); iss_set_error("cudaMemcpy f16 weights: %s", cudaGetErrorString(e)); return ISS_ERR_CUDA; }
+    *d_out = d; *inv_scale = 1.f / scale;
+    return ISS_OK;
 }

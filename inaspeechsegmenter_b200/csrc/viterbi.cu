@@ -15,6 +15,9 @@
 // associative and exact -- is parallel: per-256-step chunk maps, a short serial
 // scan over chunk maps, then all chunks emit their states concurrently.
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
 #include <vector>
 
 #include "iss_common.cuh"
@@ -42,6 +45,7 @@ struct VitLayout {
     const double *vin;             // [n_seg][MAXK] incoming scores (continue from a predecessor) or nullptr
     double *vout;                  // [n_seg][MAXK] outgoing scores V[T-1] or nullptr
     int alias;                     // 1: every block walks the SAME range seg_off[0..1] (basis chains of a transfer matrix)
+                                   // 2: block b walks segment b / 2 with vin / vout slot b (two basis chains per segment)
     int store_bp;                  // 0: scores only
 };
 
@@ -55,9 +59,10 @@ template <int K, bool ENERGY>
 __global__ void __launch_bounds__(32)
 viterbi_forward_kernel(const float *__restrict__ src, const double *__restrict__ stats, VitParams prm, VitLayout lay)
 {
-    const int seg = blockIdx.x, lane = threadIdx.x;
-    const int64_t t0 = lay.alias ? lay.seg_off[0] : lay.seg_off[seg];
-    const int64_t T = (lay.alias ? lay.seg_off[1] : lay.seg_off[seg + 1]) - t0;
+    const int slot = blockIdx.x, lane = threadIdx.x;             // slot indexes vin / vout / last
+    const int seg = lay.alias == 1 ? 0 : (lay.alias == 2 ? slot >> 1 : slot);
+    const int64_t t0 = lay.seg_off[seg];
+    const int64_t T = lay.seg_off[seg + 1] - t0;
     if (T <= 0) return;
     const bool cont = lay.vin != nullptr;          // first step is an ordinary transition from vin
     double thr = 0.0;
@@ -69,7 +74,7 @@ viterbi_forward_kernel(const float *__restrict__ src, const double *__restrict__
     }
     double V[K];
 #pragma unroll
-    for (int j = 0; j < K; ++j) V[j] = cont ? lay.vin[seg * MAXK + j] : 0.0;
+    for (int j = 0; j < K; ++j) V[j] = cont ? lay.vin[slot * MAXK + j] : 0.0;
 
     for (int64_t base = 0; base < T; base += 32) {
         const int64_t t = base + lane;
@@ -151,10 +156,10 @@ viterbi_forward_kernel(const float *__restrict__ src, const double *__restrict__
             best = u ? V[k] : best;
             arg = u ? k : arg;
         }
-        if (lay.store_bp) lay.last[seg] = (uint8_t)arg;
+        if (lay.store_bp) lay.last[slot] = (uint8_t)arg;
         if (lay.vout) {
 #pragma unroll
-            for (int k = 0; k < K; ++k) lay.vout[seg * MAXK + k] = V[k];
+            for (int k = 0; k < K; ++k) lay.vout[slot * MAXK + k] = V[k];
         }
     }
 }
@@ -389,11 +394,97 @@ extern "C" int iss_energy_emit(iss_ctx *ctx, int64_t L, int end_state, int out_s
     return ISS_OK;
 }
 
+// ---- chunk-parallel energy Viterbi ------------------------------------------------------------------------
+// The whole-file chain (3.6 M frames per 10 h, ~40 ns per frame when walked serially = 6-9 % of a step) is cut
+// into chunks of ECH frames that are walked CONCURRENTLY, exactly as shard.py cuts it at rank boundaries:
+//   1. chunk 0: its true forward pass (scores out);  chunks 1..C-1: the 2x2 max-plus transfer matrix of the
+//      chunk (two basis-vector chains per chunk)                                    -- 2C - 1 concurrent chains
+//   2. one thread composes the entry scores  entry[c+1][j] = max_i(entry[c][i] + M_c[j][i])
+//   3. chunks 1..C-1: true forward pass from their entry scores (back-pointers stored)   -- C - 1 chains
+//   4. the usual parallel backtrack over the whole sequence.
+// Exact in exact arithmetic; in IEEE double the entry scores are associated differently from the serial chain
+// (one addition of a chunk-relative score instead of ECH stepwise additions), which could only matter for a
+// path tie closer than ~1e-8 -- the path scores are sums of a handful of constants (-5, -345.39, -23.03, -1e-10)
+// whose distinct combinations are orders of magnitude further apart.  The serial kernel stays available
+// (ISS_B200_VITERBI=serial, and it is what the GPU tests compare this against on 10 h tracks).
+constexpr int64_t ECH = 16384;
+
+__global__ void energy_entry_compose_kernel(const double *__restrict__ v0, const double *__restrict__ basis_out,
+                                            int nchunk, double *__restrict__ entry)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double e0 = v0[0], e1 = v0[1];                               // scores leaving chunk 0 = entering chunk 1
+    for (int c = 1; c < nchunk; ++c) {
+        entry[(c - 1) * MAXK + 0] = e0; entry[(c - 1) * MAXK + 1] = e1;
+        // basis_out slot 2(c-1)+i = scores leaving chunk c when entering in state i with score 0
+        const double *m0 = basis_out + (size_t)(2 * (c - 1)) * MAXK, *m1 = m0 + MAXK;
+        const double a0 = e0 + m0[0], b0 = e1 + m1[0], a1 = e0 + m0[1], b1 = e1 + m1[1];
+        e0 = (b0 > a0) ? b0 : a0;
+        e1 = (b1 > a1) ? b1 : a1;
+    }
+}
+
+static int g_energy_serial = -1;        // -1: read ISS_B200_VITERBI on first use
+static bool energy_serial()
+{
+    if (g_energy_serial < 0) { const char *e = getenv("ISS_B200_VITERBI"); g_energy_serial = (e && !strcmp(e, "serial")) ? 1 : 0; }
+    return g_energy_serial == 1;
+}
+extern "C" int iss_set_energy_viterbi_serial(int serial) { g_energy_serial = serial ? 1 : 0; return ISS_OK; }
+
+static int energy_viterbi_chunked(iss_ctx *ctx, const float *d_loge, int64_t L, const double *d_loge_stats, const VitParams &prm,
+                                  int out_stride, uint8_t *d_states, void *d_work, cudaStream_t st)
+{
+    const int C = (int)((L + ECH - 1) / ECH);
+    // backtrack layout: ONE sequence [0, L)
+    const int64_t off1[2] = {0, L};
+    HostPlan hp1; VitLayout lay1 = {};
+    int rc = make_layout(off1, 1, d_work, hp1, lay1, st);
+    if (rc != ISS_OK) return rc;
+    // forward layout: C segments over the same back-pointer array, tables behind lay1's
+    uint8_t *p = lay1.last + 256;
+    size_t o = 0;
+    std::vector<int64_t> seg(C + 1);
+    for (int c = 0; c <= C; ++c) seg[c] = std::min<int64_t>((int64_t)c * ECH, L);
+    VitLayout lay = lay1;
+    lay.seg_off = reinterpret_cast<int64_t *>(p + o); o = align_up(o + sizeof(int64_t) * (C + 1), 256);
+    lay.last = p + o;                                  o = align_up(o + (size_t)2 * C, 256);
+    double *d_v0 = reinterpret_cast<double *>(p + o);  o += sizeof(double) * MAXK;
+    double *d_basis_in = reinterpret_cast<double *>(p + o);  o += sizeof(double) * MAXK * 2 * C;
+    double *d_basis_out = reinterpret_cast<double *>(p + o); o += sizeof(double) * MAXK * 2 * C;
+    double *d_entry = reinterpret_cast<double *>(p + o);     o += sizeof(double) * MAXK * C;
+    ISS_CUDA_OK(cudaMemcpyAsync(lay.seg_off, seg.data(), sizeof(int64_t) * (C + 1), cudaMemcpyHostToDevice, st));
+    std::vector<double> basis((size_t)MAXK * 2 * C, 0.0);
+    for (int c = 0; c < C; ++c) {                                // e_0 = (0, -inf), e_1 = (-inf, 0) in max-plus
+        basis[(size_t)(2 * c) * MAXK + 1] = -INFINITY;
+        basis[(size_t)(2 * c + 1) * MAXK + 0] = -INFINITY;
+    }
+    ISS_CUDA_OK(cudaMemcpyAsync(d_basis_in, basis.data(), sizeof(double) * basis.size(), cudaMemcpyHostToDevice, st));
+    // 1a. chunk 0, true pass (prior on the first frame), back-pointers stored
+    VitLayout l0 = lay; l0.vin = nullptr; l0.vout = d_v0; l0.alias = 0; l0.store_bp = 1;
+    viterbi_forward_kernel<2, true><<<1, 32, 0, st>>>(d_loge, d_loge_stats, prm, l0);
+    // 1b. chunks 1..C-1: two basis chains each (segment index = 1 + slot / 2 => shift the offset table by one)
+    VitLayout lb = lay; lb.seg_off = lay.seg_off + 1; lb.vin = d_basis_in; lb.vout = d_basis_out; lb.alias = 2; lb.store_bp = 0;
+    viterbi_forward_kernel<2, true><<<2 * (C - 1), 32, 0, st>>>(d_loge, d_loge_stats, prm, lb);
+    // 2. entry scores of chunks 1..C-1
+    energy_entry_compose_kernel<<<1, 32, 0, st>>>(d_v0, d_basis_out, C, d_entry);
+    // 3. chunks 1..C-1, true pass from their entry scores
+    VitLayout lt = lay; lt.seg_off = lay.seg_off + 1; lt.vin = d_entry; lt.vout = nullptr; lt.alias = 0; lt.store_bp = 1;
+    lt.last = lay.last + 1;                                      // last[c] = argmax V at the end of chunk c
+    viterbi_forward_kernel<2, true><<<C - 1, 32, 0, st>>>(d_loge, d_loge_stats, prm, lt);
+    ISS_CUDA_OK(cudaGetLastError());
+    iss_count_launch(4);
+    // 4. backtrack over the whole sequence from the final chunk's argmax
+    lay1.last = lay.last + (C - 1);
+    return run_backtrack(lay1, hp1, 1, out_stride, d_states, st);
+}
+
 extern "C" int64_t iss_viterbi_work_bytes(int64_t total_steps, int n_seg)
 {
     if (total_steps < 0 || n_seg < 0) return -1;
     const int64_t nc = total_steps / CH + n_seg + 1;
-    return total_steps + 2 * nc + 2 * (int64_t)sizeof(int64_t) * (n_seg + 1) + n_seg + 8 * 256 + 1024 /* vin/vout/map scratch */;
+    const int64_t chunked = (total_steps / ECH + 2) * 256 + 8192;         // tables of the chunk-parallel energy pass
+    return total_steps + 2 * nc + 2 * (int64_t)sizeof(int64_t) * (n_seg + 1) + n_seg + 8 * 256 + 1024 /* vin/vout/map scratch */ + chunked;
 }
 
 extern "C" int iss_energy_viterbi(iss_ctx *ctx, const float *d_loge, int64_t L, const double *d_loge_stats,
@@ -415,6 +506,7 @@ extern "C" int iss_energy_viterbi(iss_ctx *ctx, const float *d_loge, int64_t L, 
     VitParams prm = {};
     for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) prm.A[i][j] = h_trans[i * 2 + j];
     prm.prior = log_prior; prm.emis_hit = h_emis[0]; prm.emis_miss = h_emis[1]; prm.log_ratio = log_ratio;
+    if (!energy_serial() && L >= 4 * ECH) return energy_viterbi_chunked(ctx, d_loge, L, d_loge_stats, prm, out_stride, d_states, d_work, st);
     viterbi_forward_kernel<2, true><<<1, 32, 0, st>>>(d_loge, d_loge_stats, prm, lay);
     ISS_CUDA_OK(cudaGetLastError());
     iss_count_launch();

@@ -13,14 +13,19 @@ GPU, torch.distributed over NCCL/NVLink as plumbing):
     (segmenter.py:70) and the energy Viterbi is a whole-file chain
     (pyannote_viterbi.py:202-220): ranks all-gather their owned loge
     (4 B/frame) and every rank evaluates the reduction + the K = 2 chain on the
-    full track (replicated: it is a serial ~12 ns/frame chain, so this costs the
-    same as computing it once, and needs no second exchange);
+    full track with the very kernels a single GPU uses (replicated: the chain is
+    chunk-parallel inside iss_energy_viterbi, a few ms per 10 h, so replication
+    costs nothing and needs no second exchange);
     (2) per-segment Viterbi of CNN posteriors: ranks all-gather the posteriors
     of their patch range (12-16 B/patch) and decode all segments, replicated.
   * every rank ends with the complete, identical segment list.
 
 Because every kernel is evaluated on exactly the same values in the same order
-as on one GPU, the sharded result is bit-identical to the single-GPU result.
+as on one GPU, the sharded result is bit-identical to the single-GPU result
+(default energy_mode 'replicated').  The opt-in energy_mode 'transfer' cuts the
+energy chain at the rank boundaries instead (max-plus transfer matrices); it is
+exact in exact arithmetic but associates the entry scores differently, so it is
+not covered by the bit-identity statement.
 
 The numeric steps sit behind a small backend interface so the orchestration
 and the collectives can be tested with world_size 2 on the gloo backend
@@ -98,17 +103,21 @@ class Comm:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.bytes = 0
 
-    def all_gather_var(self, t):
-        """Concatenation (rank order) of per-rank tensors whose first dimension differs."""
+    def all_gather_var(self, t, counts=None):
+        """Concatenation (rank order) of per-rank tensors whose first dimension differs.  `counts` (the
+        per-rank lengths, when every rank can derive them from the plan) skips the length exchange and
+        its host synchronisation."""
         if self.world == 1:
             return t
         if t.is_cuda and dist.get_backend(self.group) == 'gloo':
             # test configuration (several ranks sharing one GPU): stage through the host
-            return Comm('cpu', self.group).all_gather_var(t.cpu()).to(t.device)
-        n = torch.tensor([t.shape[0]], dtype=torch.int64, device=self.device)
-        counts = [torch.zeros_like(n) for _ in range(self.world)]
-        dist.all_gather(counts, n, group=self.group)
-        counts = [int(c.item()) for c in counts]
+            return Comm('cpu', self.group).all_gather_var(t.cpu(), counts).to(t.device)
+        if counts is None:
+            n = torch.tensor([t.shape[0]], dtype=torch.int64, device=self.device)
+            cl = [torch.zeros_like(n) for _ in range(self.world)]
+            dist.all_gather(cl, n, group=self.group)
+            counts = [int(c.item()) for c in cl]
+        assert counts[self.rank] == t.shape[0], (counts, self.rank, t.shape)
         m = max(counts)
         pad = torch.zeros((m,) + tuple(t.shape[1:]), dtype=t.dtype, device=self.device)
         pad[:t.shape[0]] = t
@@ -189,7 +198,8 @@ def _dnn_stage(backend, comm, plan, rank, which, spec, mspec_local, lseg):
     el, er = plan.edges(rank)
     ranges = plan.local_ranges(rank, lseg, spec.inlabel)
     probs_loc = backend.cnn_probs(which, mspec_local, ranges, el, er)
-    probs = comm.all_gather_var(probs_loc)
+    counts = [sum(b - a for a, b in plan.local_ranges(r, lseg, spec.inlabel)) for r in range(comm.world)]
+    probs = comm.all_gather_var(probs_loc, counts)
     sel = [(a, b) for lab, a, b in lseg if lab == spec.inlabel]
     if not sel:
         return list(lseg)
@@ -271,11 +281,11 @@ def segment_sharded(backend, comm, plan, pcm_local, vad_spec, gender_spec=None, 
     assert len(loge) == fb - fa, (len(loge), fa, fb)
     oa, ob = plan.owned_frames(rank)
     loge_own = loge[oa - fa:ob - fa].contiguous()
-    loge_global = comm.all_gather_var(loge_own)
+    loge_global = comm.all_gather_var(loge_own, [plan.owned_frames(r)[1] - plan.owned_frames(r)[0] for r in range(comm.world)])
     assert loge_global.shape[0] == plan.L
     mode = getattr(plan, 'energy_mode', 'auto')
     if mode == 'auto':
-        mode = 'transfer' if comm.world >= 3 else 'replicated'
+        mode = 'replicated'
     if comm.world == 1 or mode == 'replicated':
         track = backend.energy_track(loge_global, energy_ratio)
     else:
@@ -290,7 +300,7 @@ def segment_sharded(backend, comm, plan, pcm_local, vad_spec, gender_spec=None, 
 
 def segment_signal_sharded(segmenter, pcm_local, n_samples_total, group=None, energy_mode='auto'):
     """Convenience wrapper for the product: `segmenter` is this rank's Segmenter.
-    energy_mode: 'replicated' | 'transfer' | 'auto' (transfer matrices from 3 ranks up)."""
+    energy_mode: 'replicated' (= 'auto': bit-identical to one GPU) | 'transfer' (chain cut at rank boundaries)."""
     comm = Comm(segmenter.ctx.device, group)
     plan = ShardPlan(n_samples_total, comm.world)
     plan.energy_mode = energy_mode

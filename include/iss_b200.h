@@ -115,7 +115,11 @@ int iss_loge_stats(iss_ctx *ctx, const float *d_loge, int64_t L, double *d_loge_
  *           from->to), prior = log_prior = log(1/2).
  * d_states: uint8 [ceil(L / out_stride)] -- state of every out_stride-th frame
  * (the reference keeps [::2], segmenter.py:262).  d_work: scratch of at least
- * iss_viterbi_work_bytes(L, 1) bytes. */
+ * iss_viterbi_work_bytes(L, 1) bytes.
+ * Tracks of >= 65536 frames are decoded chunk-parallel (16384-frame chunks: max-plus transfer
+ * matrices -> entry scores -> concurrent true passes); iss_set_energy_viterbi_serial(1), or
+ * ISS_B200_VITERBI=serial, forces the single serial chain (the checker of the GPU tests). */
+int iss_set_energy_viterbi_serial(int serial);
 int iss_energy_viterbi(iss_ctx *ctx, const float *d_loge, int64_t L, const double *d_loge_stats,
                        double log_ratio, const double *h_emis, const double *h_trans,
                        double log_prior, int out_stride, uint8_t *d_states, void *d_work,

@@ -135,6 +135,45 @@ def test_k3_energy_viterbi_full_track_vs_oracle(rt):
         assert np.array_equal(got, ref[::stride].astype(np.uint8))
 
 
+@pytest.mark.parametrize('L,seed', [(70001, 1), (16384 * 5, 2), (16384 * 5 + 1, 3), (3600037, 4)])
+def test_k3_energy_viterbi_chunk_parallel_equals_serial_chain(rt, L, seed):
+    """The chunk-parallel energy decode (16384-frame chunks, max-plus transfer matrices) against the serial
+    chain kernel on tracks up to 10 h (3.6 M frames), and against the reference-pinned C oracle on the shorter ones:
+    activity bursts of every length, frames sitting within a few ulps of the threshold, -inf (silent) frames."""
+    from oracle import segmenter_oracle as so
+    rng = np.random.default_rng(seed)
+    lo = np.empty(L, dtype=np.float32)
+    pos = 0
+    while pos < L:                                              # alternating quiet / active runs, 1 frame .. 40 s
+        n = int(min(L - pos, rng.choice([1, 2, 3, 7, 40, 300, 4000]) * (1 + rng.integers(0, 3))))
+        level = rng.choice([-14.0, -9.0, -3.0, 1.5])
+        lo[pos:pos + n] = level + rng.normal(0, 1.0, n)
+        pos += n
+    fin_mean = float(np.mean(lo))
+    thr = np.float32(fin_mean + np.log(0.03))
+    near = rng.integers(0, L, 2000)
+    lo[near] = np.nextafter(np.full(2000, thr, dtype=np.float32), (np.inf * rng.choice([-1.0, 1.0], 2000)).astype(np.float32))   # +-1 ulp around the threshold
+    lo[rng.integers(0, L, 500)] = -np.inf
+    loge = torch.from_numpy(lo).cuda()
+    eng, lib = rt['engine'], rt['lib'].load()
+    stats = eng.loge_stats(rt['ctx'], loge)
+    try:
+        lib.iss_set_energy_viterbi_serial(1)
+        serial = eng.energy_viterbi(rt['ctx'], loge, stats, 0.03, out_stride=1).cpu().numpy()
+        lib.iss_set_energy_viterbi_serial(0)
+        chunked = eng.energy_viterbi(rt['ctx'], loge, stats, 0.03, out_stride=1).cpu().numpy()
+        chunked2 = eng.energy_viterbi(rt['ctx'], loge, stats, 0.03, out_stride=2).cpu().numpy()
+    finally:
+        lib.iss_set_energy_viterbi_serial(0)
+    assert np.array_equal(chunked, serial)
+    assert np.array_equal(chunked2, serial[::2])
+    assert 0 < serial.mean() < 1
+    if L < 200000:
+        ref = so.energy_activity(lo, 0.03)
+        assert np.array_equal(serial, ref.astype(np.uint8))
+    REPORT['k3_energy_chunked_L%d' % L] = dict(identical_to_serial=True, frames=int(L), active=float(serial.mean()))
+
+
 def test_k3_segments_golden_and_random(rt, golden):
     from oracle import viterbi_oracle as vo
     eng = rt['engine']

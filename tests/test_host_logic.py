@@ -178,7 +178,7 @@ def test_bench_reference_arm_contract():
     import subprocess
     import sys
     out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '1',
-                          '--cpu-sample-sec', '4'], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+                          '--cpu-chunk-sec', '6'], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     line = [l for l in out.stdout.splitlines() if l.startswith('{')][-1]
     d = json.loads(line)
