@@ -48,6 +48,7 @@ struct iss_cnn {
     int n_classes;
     int64_t max_act;       // largest per-patch activation (floats) over all layer outputs
     double flops;
+    double *d_first_S = nullptr;   // [cout of layer 0] float64 sums of the first layer's filter taps (FirstFuse)
     // live profiling of one layer (bench.py roofline)
     int prof_layer = -1;
     std::vector<cudaEvent_t> prof_ev;      // pairs: [2i] start, [2i+1] stop
@@ -201,6 +202,40 @@ conv_first_direct_kernel(const FirstArgs a)
             }
         }
     }
+}
+
+// ------------------------------------------------------------------ first layer by linearity (FirstFuse, conv_gemm.cuh)
+// Y[r][x][c] = sum_{kh,kw} w[kh][kw][c] * mspec[f0 + r + kh][x + kw] in float64, for the frames a batch of patches
+// covers; one thread = one (row, column) position and 4 channels, filter in shared memory.
+__global__ void __launch_bounds__(256)
+first_linear_kernel(const float *__restrict__ mspec, int ld, int64_t f0, int64_t rows, int64_t n_frames, int OW, int KH, int KW, int C,
+                    const float *__restrict__ w, double *__restrict__ Y)
+{
+    extern __shared__ __align__(16) float wsm[];               // [KH * KW][C]
+    for (int i = threadIdx.x; i < KH * KW * C; i += 256) wsm[i] = w[i];
+    __syncthreads();
+    const int CQ = C >> 2;
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;  // over [row][x][c / 4]
+    if (i >= rows * OW * CQ) return;
+    const int c4 = (int)(i % CQ);
+    const int64_t rx = i / CQ;
+    const int x = (int)(rx % OW);
+    const int64_t r = rx / OW;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int kh = 0; kh < KH; ++kh) {
+        const int64_t f = f0 + r + kh;
+        if (f >= n_frames) continue;                            // rows past the last frame are never read by a patch
+        const float *src = mspec + f * ld + x;
+        for (int kw = 0; kw < KW; ++kw) {
+            const double xv = (double)__ldg(src + kw);
+            const float4 w4 = *reinterpret_cast<const float4 *>(wsm + (kh * KW + kw) * C + c4 * 4);
+            acc[0] = fma(xv, (double)w4.x, acc[0]); acc[1] = fma(xv, (double)w4.y, acc[1]);
+            acc[2] = fma(xv, (double)w4.z, acc[2]); acc[3] = fma(xv, (double)w4.w, acc[3]);
+        }
+    }
+    double2 *dst = reinterpret_cast<double2 *>(Y + (r * OW + x) * (int64_t)C + c4 * 4);
+    dst[0] = make_double2(acc[0], acc[1]);
+    dst[1] = make_double2(acc[2], acc[3]);
 }
 
 // ------------------------------------------------------------------ max pooling (NHWC)
@@ -398,6 +433,17 @@ extern "C" int iss_cnn_create(iss_ctx *ctx, const iss_layer_desc *layers, int n_
             if (rc != ISS_OK) { iss_cnn_destroy(m); return rc; }
         }
     }
+    {   // S_c = sum of the first layer's taps (float64), for the fused first layer
+        const iss_layer_desc &d0 = m->layers[0].d;
+        if (d0.kind == ISS_LAYER_CONV2D && d0.cin == 1) {
+            std::vector<double> S(d0.cout, 0.0);
+            for (int t = 0; t < d0.kh * d0.kw; ++t)
+                for (int c = 0; c < d0.cout; ++c) S[c] += (double)h_blob[d0.w_off + (int64_t)t * d0.cout + c];
+            e = cudaMalloc(&m->d_first_S, sizeof(double) * d0.cout);
+            if (e == cudaSuccess) e = cudaMemcpy(m->d_first_S, S.data(), sizeof(double) * d0.cout, cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) { iss_cnn_destroy(m); iss_set_error("first-layer sums: %s", cudaGetErrorString(e)); return ISS_ERR_CUDA; }
+        }
+    }
     *out = m;
     return ISS_OK;
 }
@@ -409,12 +455,25 @@ extern "C" int iss_cnn_destroy(iss_cnn *cnn)
     for (cudaEvent_t ev : cnn->prof_ev) cudaEventDestroy(ev);
     for (Layer &L : cnn->layers) { if (L.d_wt) cudaFree(L.d_wt); if (L.d_wt_f16) cudaFree(L.d_wt_f16); }
     if (cnn->d_blob) cudaFree(cnn->d_blob);
+    if (cnn->d_first_S) cudaFree(cnn->d_first_S);
     delete cnn;
     return ISS_OK;
 }
 
 extern "C" int iss_cnn_num_classes(const iss_cnn *cnn) { return cnn ? cnn->n_classes : -1; }
 extern "C" double iss_cnn_flops_per_patch(const iss_cnn *cnn) { return cnn ? cnn->flops : 0.0; }
+
+namespace {
+// rows of the float64 first-layer map a batch of B patches may need (3x the contiguous case; batches whose
+// patches are spread wider fall back to the un-fused first layer) and its size in bytes (0: no fusion possible)
+int64_t first_y_rows(int64_t B) { return 3 * (PATCH_HOP * B + PATCH_H); }
+size_t first_y_bytes(const iss_cnn *cnn, int64_t B)
+{
+    if (!cnn->d_first_S || cnn->layers.size() < 2) return 0;
+    const Layer &L0 = cnn->layers[0];
+    return align_up((size_t)first_y_rows(B) * L0.out_w * L0.out_c * sizeof(double), 256);
+}
+}  // namespace
 
 extern "C" int64_t iss_cnn_workspace_bytes(const iss_cnn *cnn, int64_t n, int n_seg)
 {
@@ -426,6 +485,7 @@ extern "C" int64_t iss_cnn_workspace_bytes(const iss_cnn *cnn, int64_t n, int n_
     bytes += align_up((size_t)n * 8 * 4, 256);             // logits [n][<=8]
     bytes += 2 * align_up((size_t)B * cnn->max_act * 4, 256);
     bytes += align_up((size_t)(n_seg + 1) * 4, 256) + align_up((size_t)(n_seg + 1) * 8, 256);   // segment tables
+    bytes += first_y_bytes(cnn, B);                                                               // float64 map of the fused first layer
     return bytes;
 }
 
@@ -510,6 +570,18 @@ extern "C" int iss_cnn_forward(iss_ctx *ctx, iss_cnn *cnn, const float *d_mspec,
     act[1] = reinterpret_cast<float *>(p + o);    o += align_up((size_t)B * cnn->max_act * 4, 256);
     int32_t *d_seg_start = reinterpret_cast<int32_t *>(p + o); o += align_up((size_t)(n_seg + 1) * 4, 256);
     int64_t *d_seg_off = reinterpret_cast<int64_t *>(p + o);   o += align_up((size_t)(n_seg + 1) * 8, 256);
+    double *d_first_y = first_y_bytes(cnn, B) ? reinterpret_cast<double *>(p + o) : nullptr;  o += first_y_bytes(cnn, B);
+    // host copy of patch_index_kernel's arithmetic: first log-mel frame of patch i (for the span of a batch)
+    auto host_row0 = [&](int64_t i) -> int64_t {
+        int lo = 0, hi = n_seg;
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (off[mid] <= i) lo = mid; else hi = mid; }
+        int64_t j = h_seg_start[lo] + (i - off[lo]) - (edge_left ? PATCH_LFILL : 0);
+        if (j < 0) j = 0;
+        if (edge_right && j > U - 1) j = U - 1;
+        return j * PATCH_HOP;
+    };
+    bool ranges_ascending = true;
+    for (int s = 1; s < n_seg; ++s) ranges_ascending = ranges_ascending && h_seg_start[s] >= h_seg_stop[s - 1];
     ISS_CUDA_OK(cudaMemcpyAsync(d_seg_start, h_seg_start, sizeof(int32_t) * n_seg, cudaMemcpyHostToDevice, st));
     ISS_CUDA_OK(cudaMemcpyAsync(d_seg_off, off.data(), sizeof(int64_t) * (n_seg + 1), cudaMemcpyHostToDevice, st));
 
@@ -525,6 +597,8 @@ extern "C" int iss_cnn_forward(iss_ctx *ctx, iss_cnn *cnn, const float *d_mspec,
         const float *cur = nullptr;
         int which = 0;
         bool cur_packed = false;                                 // format of `cur`: fp32 values or split-half words
+        FirstFuse ffuse = {};                                    // set by layer 0 when it is folded into layer 1's slab fill
+        bool first_fused = false;
         for (size_t li = 0; li < cnn->layers.size(); ++li) {
             const Layer &Lr = cnn->layers[li];
             const iss_layer_desc &d = Lr.d;
@@ -577,7 +651,32 @@ extern "C" int iss_cnn_forward(iss_ctx *ctx, iss_cnn *cnn, const float *d_mspec,
                 ISS_REQUIRE(!a.in_packed || (li > 0 && iss_conv_f16_slab_covers(a)), ISS_ERR_UNSUPPORTED,
                             "iss_cnn_forward: layer %d was handed split-half words it cannot read", (int)li);
                 int rc;
-                if (li == 0) {
+                // Fold the first layer into the next convolution's slab fill (FirstFuse, conv_gemm.cuh)?  Needs: the direct
+                // first-layer shape without padding / stride, a packed-input slab convolution right behind it, and a batch
+                // whose patches span few enough frames for the float64 map.
+                const char *fuse_env = getenv("ISS_B200_FUSE_FIRST");      // "0" = keep the stand-alone first-layer kernel (A/B tests)
+                const bool fuse_off = fuse_env && fuse_env[0] == '0';
+                if (li == 0 && direct && a.out_packed && !fuse_off && d_first_y && ranges_ascending && cnn->layers.size() > 1 &&
+                    cnn->layers[1].d.kind == ISS_LAYER_CONV2D && d.sh == 1 && d.sw == 1 && d.pad_top == 0 && d.pad_left == 0 &&
+                    d.pad_bottom == 0 && d.pad_right == 0 && !(d.flags & ISS_F_SOFTMAX)) {
+                    const int64_t f_first = host_row0(b0), f_last = host_row0(b0 + nb - 1);
+                    const int64_t rows = f_last - f_first + Lr.out_h;
+                    if (rows <= first_y_rows(B)) {
+                        const int64_t work = rows * Lr.out_w * (d.cout >> 2);
+                        first_linear_kernel<<<(unsigned)((work + 255) / 256), 256, (size_t)d.kh * d.kw * d.cout * sizeof(float), st>>>(
+                            d_mspec, ld, f_first, rows, L, Lr.out_w, d.kh, d.kw, d.cout, a.w, d_first_y);
+                        ISS_CUDA_OK(cudaGetLastError());
+                        iss_count_launch();
+                        ffuse.Y = d_first_y; ffuse.y_f0 = f_first; ffuse.y_rows = rows;
+                        ffuse.row0 = pa.row0 + b0; ffuse.mu = pa.mu + b0; ffuse.sigma = pa.sigma + b0; ffuse.S = cnn->d_first_S;
+                        ffuse.bias = a.bias; ffuse.pre_scale = a.pre_scale; ffuse.pre_shift = a.pre_shift;
+                        ffuse.post_scale = a.post_scale; ffuse.post_shift = a.post_shift; ffuse.flags = a.flags; ffuse.n_img = nb;
+                        first_fused = true;
+                    }
+                }
+                if (li == 0 && first_fused) {
+                    rc = ISS_OK;                                  // nothing stored: layer 1 reads the map
+                } else if (li == 0) {
                     ISS_REQUIRE(d.kind == ISS_LAYER_CONV2D, ISS_ERR_UNSUPPORTED, "iss_cnn_forward: first layer must be Conv2D");
                     if (direct) {
                         FirstArgs f = {};
@@ -603,6 +702,7 @@ extern "C" int iss_cnn_forward(iss_ctx *ctx, iss_cnn *cnn, const float *d_mspec,
                     }
                 } else {
                     a.in = cur;
+                    if (li == 1 && first_fused) { a.first = &ffuse; a.in = nullptr; a.in_packed = 1; }
                     rc = iss_launch_conv(a, false, st);
                 }
                 if (rc != ISS_OK) return rc;

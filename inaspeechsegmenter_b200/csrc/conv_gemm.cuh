@@ -19,6 +19,26 @@ __device__ __forceinline__ float iss_unpack_split(uint32_t w)
 
 #define ISS_F_RESIDUAL 64     /* internal: + residual[m][n] after the pre-affine, before ReLU */
 
+// First layer folded into the slab fill of the convolution behind it (conv_gemm_tc_f16.cu, FIRST mode): the
+// first Conv2D of the segmenter CNNs has ONE input channel and its input is the z-normalised patch
+// (x - mu_j) / sigma_j (segmenter.py:82), so by linearity
+//     conv(x^)[t, f, c] = (Y[row0_j + t, f, c] - mu_j * S_c) / sigma_j,   Y = conv(raw log-mel), S_c = sum of the filter
+// and Y is shared by all the patches that overlap a frame (97 % overlap: hop 2 of 68 frames).  Y is computed once
+// per batch in float64 (first_linear_kernel); the slab fill of the next convolution evaluates the expression
+// above + the first layer's bias / BatchNorm / ReLU epilogue and writes split-half words straight into shared
+// memory: the first layer's output (283 KB per patch, 47 % of all activation traffic) never exists in HBM.
+struct FirstFuse {
+    const double *Y;                // [y_rows][W * C] float64, row r = conv of log-mel frames y_f0 + r ..
+    int64_t y_f0;                   // log-mel frame of Y row 0
+    int64_t y_rows;
+    const int32_t *row0;            // per patch of the batch: first log-mel frame
+    const float *mu, *sigma;        // per patch: statistics of the patch (float32, as the reference computes them)
+    const double *S;                // [C] sum of the first layer's filter taps, float64
+    const float *bias, *pre_scale, *pre_shift, *post_scale, *post_shift;   // first layer's epilogue (nullptr = absent)
+    int flags;                      // ISS_F_* of the first layer
+    int64_t n_img;                  // patches in the batch
+};
+
 struct ConvArgs {
     const float *in;        // NHWC activations, or the log-mel rows when `first`
     const float *w;         // [K][N]
@@ -40,9 +60,11 @@ struct ConvArgs {
     const void *wt_f16; float wt_f16_inv_scale;
     // activation formats of that engine: fp32 values (0) or split-half words lo16 << 16 | hi16 (1)
     int in_packed, out_packed;
+    const FirstFuse *first;         // host pointer, non-null: FIRST mode (copied into the kernel parameters)
     // slab kernel (conv_gemm_tc_f16.cu) only, filled in by iss_launch_conv_tc_f16
     int slab_R;             // output rows (of width OW) per 128-row GEMM tile
     int slab_rows;          // input rows the slab is sized for
+    int slab_tpi;           // > 0: tiles per image (tiles never straddle images); 0: tiles over the global row sequence
     int64_t in_elems;       // floats in `in` (loads past the end are zero-filled)
 };
 

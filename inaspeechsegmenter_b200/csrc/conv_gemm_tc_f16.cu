@@ -83,11 +83,17 @@ __device__ __forceinline__ uint4 lds128u(uint32_t addr)
     return v;
 }
 
-// PACKED: the input tensor holds split-half words (see the file header); a.out_packed selects the output format.
-template <int BN, int SB, int ST, bool PACKED>
+// MODE: how the input slab is obtained -- IN_F32: fp32 activations, split in the A producers; IN_PACKED: split-half
+// words (see the file header); IN_FIRST: the layer in front is the one-channel first convolution of a segmenter CNN
+// and is evaluated INSIDE the slab fill from the shared float64 map Y (FirstFuse, conv_gemm.cuh) -- the slab then
+// holds split-half words like IN_PACKED.  a.out_packed selects the output format.
+constexpr int IN_F32 = 0, IN_PACKED = 1, IN_FIRST = 2;
+
+template <int BN, int SB, int ST, int MODE>
 __global__ void __launch_bounds__(160, (TcHCfg<BN, SB, ST>::TMEM_COLS <= 256 ? 2 : 1))
-conv_gemm_tc3h_kernel(const ConvArgs a, const F16Args h)
+conv_gemm_tc3h_kernel(const ConvArgs a, const F16Args h, const FirstFuse ff)
 {
+    constexpr bool PACKED = MODE != IN_F32;
     using Cfg = TcHCfg<BN, SB, ST>;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -103,11 +109,23 @@ conv_gemm_tc3h_kernel(const ConvArgs a, const F16Args h)
     const int nkb = a.K / HBK;
     const int R = a.slab_R, KH1 = a.KH - 1;
     const int64_t Q = a.M / a.OW;
-    const int64_t q0 = (int64_t)blockIdx.x * R;
+    // tile -> output rows [q0, q0 + nq) of the global row sequence q = img * OH + oh.  slab_tpi > 0: tiles never
+    // straddle images (tile t of image img covers rows t*R ..), which keeps the slab at R + KH - 1 rows; otherwise
+    // tiles are R consecutive rows of the whole sequence and may straddle an image boundary.
+    int64_t q0, img0;
+    int nq;
+    if (a.slab_tpi > 0) {
+        img0 = blockIdx.x / a.slab_tpi;
+        const int oh0 = (int)(blockIdx.x - img0 * a.slab_tpi) * R;
+        q0 = img0 * a.OH + oh0;
+        nq = (a.OH - oh0) < R ? (a.OH - oh0) : R;
+    } else {
+        q0 = (int64_t)blockIdx.x * R;
+        nq = (int)((Q - q0) < (int64_t)R ? (Q - q0) : (int64_t)R);
+        img0 = q0 / a.OH;
+    }
     const int64_t mbase = q0 * a.OW;
-    const int nq = (int)((Q - q0) < (int64_t)R ? (Q - q0) : (int64_t)R);
     const int valid = nq * a.OW;
-    const int64_t img0 = q0 / a.OH;
 
     if (tid == 0) {
         for (int s = 0; s < ST; ++s) { mbar_init(&fullA[s], 4); mbar_init(&emptyA[s], 1); }
@@ -140,13 +158,57 @@ conv_gemm_tc3h_kernel(const ConvArgs a, const F16Args h)
             const int total = rows * a.W * cpp;
             int p = tid / cpp, j = tid - p * cpp;
             const int dp = 128 / cpp, dj = 128 - dp * cpp;
-            for (int q = tid; q < total; q += 128) {
-                const uint32_t dst = slab_u32 + (uint32_t)p * pix_bytes + (uint32_t)(((j & ~7) | ((j ^ p) & 7)) << 4);
-                const bool ok = q < avail;
-                cp_async16_u32(dst, src0 + (ok ? (size_t)q * 4 : 0), ok ? 16 : 0);
-                p += dp; j += dj;
-                if (j >= cpp) { j -= cpp; ++p; }
-            }
+            if constexpr (MODE == IN_FIRST) {
+                // per-image constants of the (at most 4) patches this slab touches: {mu, 1 / sigma} in float64, Y row of its row 0
+                double *tabd = reinterpret_cast<double *>(bars + 2 * ST + 2 * SB + 2);         // [4][2]
+                int64_t *tabr = reinterpret_cast<int64_t *>(tabd + 8);                           // [4]
+                if (tid < 4) {
+                    const int64_t img = img0 + tid;
+                    double mu = 0.0, inv = 0.0;
+                    int64_t yr = -1;
+                    if (img < ff.n_img) {
+                        mu = (double)ff.mu[img];
+                        inv = 1.0 / (double)ff.sigma[img];
+                        yr = (int64_t)ff.row0[img] - ff.y_f0;
+                    }
+                    tabd[2 * tid] = mu; tabd[2 * tid + 1] = inv; tabr[tid] = yr;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int f_flags = ff.flags;
+                const int row_len = a.W * a.C;                   // doubles per Y row
+                for (int q = tid; q < total; q += 128) {
+                    const uint32_t dst = slab_u32 + (uint32_t)p * pix_bytes + (uint32_t)(((j & ~7) | ((j ^ p) & 7)) << 4);
+                    const int srow = p / a.W, x = p - srow * a.W;
+                    const int64_t g = g0 + srow;                  // input row in the global (image-major) row sequence
+                    const int64_t img = g / a.H;
+                    const int ih = (int)(g - img * a.H);
+                    const int ti = (int)(img - img0);
+                    uint4 wd = make_uint4(0u, 0u, 0u, 0u);
+                    if (ti < 4 && tabr[ti] >= 0) {
+                        const double mu = tabd[2 * ti], inv = tabd[2 * ti + 1];
+                        const double *yp = ff.Y + (tabr[ti] + ih) * (int64_t)row_len + (int64_t)x * a.C + j * 4;
+                        const double2 y01 = __ldg(reinterpret_cast<const double2 *>(yp));
+                        const double2 y23 = __ldg(reinterpret_cast<const double2 *>(yp) + 1);
+                        const double yv[4] = {y01.x, y01.y, y23.x, y23.y};
+                        uint32_t w4[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int c = j * 4 + e;
+                            float v = (float)((yv[e] - mu * __ldg(ff.S + c)) * inv);
+                            if (f_flags & ISS_F_BIAS) v += __ldg(ff.bias + c);
+                            if (f_flags & ISS_F_AFFINE_PRE) v = fmaf(v, __ldg(ff.pre_scale + c), __ldg(ff.pre_shift + c));
+                            if (f_flags & ISS_F_RELU) v = fmaxf(v, 0.f);
+                            if (f_flags & ISS_F_SIGMOID) v = 1.f / (1.f + expf(-v));
+                            if (f_flags & ISS_F_AFFINE_POST) v = fmaf(v, __ldg(ff.post_scale + c), __ldg(ff.post_shift + c));
+                            w4[e] = iss_pack_split(v);
+                        }
+                        wd = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                    }
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(wd.x), "r"(wd.y), "r"(wd.z), "r"(wd.w) : "memory");
+                    p += dp; j += dj;
+                    if (j >= cpp) { j -= cpp; ++p; }
+                }
+            } else
             cp_async_commit();
             cp_async_wait<0>();
             asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -336,17 +398,19 @@ conv_gemm_tc3h_kernel(const ConvArgs a, const F16Args h)
 constexpr int SMEM_CTA_MAX = 232448;
 constexpr int SMEM_HALF_SM = 115712;
 
-template <int BN, int SB, int ST, bool PACKED>
+template <int BN, int SB, int ST, int MODE>
 int launch_tc3h_p(const ConvArgs &a, const F16Args &h, int slab_bytes, cudaStream_t st)
 {
     using Cfg = TcHCfg<BN, SB, ST>;
-    auto kern = conv_gemm_tc3h_kernel<BN, SB, ST, PACKED>;
+    auto kern = conv_gemm_tc3h_kernel<BN, SB, ST, MODE>;
     ISS_CUDA_OK(iss_optin_smem(reinterpret_cast<const void *>(kern), SMEM_CTA_MAX));
     const int64_t Q = a.M / a.OW;
-    const int64_t gm = (Q + a.slab_R - 1) / a.slab_R;
+    const int64_t gm = a.slab_tpi > 0 ? (Q / a.OH) * a.slab_tpi : (Q + a.slab_R - 1) / a.slab_R;
     ISS_REQUIRE(gm < (1ll << 31), ISS_ERR_INVALID, "conv_tc_f16: M too large");
     dim3 grid((unsigned)gm, (unsigned)(a.N / BN));
-    kern<<<grid, Cfg::THREADS, Cfg::FIXED + slab_bytes, st>>>(a, h);
+    FirstFuse ff = {};
+    if (a.first) ff = *a.first;
+    kern<<<grid, Cfg::THREADS, Cfg::FIXED + slab_bytes, st>>>(a, h, ff);
     ISS_CUDA_OK(cudaGetLastError());
     iss_count_launch();
     return ISS_OK;
@@ -355,19 +419,39 @@ int launch_tc3h_p(const ConvArgs &a, const F16Args &h, int slab_bytes, cudaStrea
 template <int BN, int SB, int ST>
 int launch_tc3h(const ConvArgs &a, const F16Args &h, int slab_bytes, cudaStream_t st)
 {
-    return a.in_packed ? launch_tc3h_p<BN, SB, ST, true>(a, h, slab_bytes, st) : launch_tc3h_p<BN, SB, ST, false>(a, h, slab_bytes, st);
+    if (a.first) return launch_tc3h_p<BN, SB, ST, IN_FIRST>(a, h, slab_bytes, st);
+    return a.in_packed ? launch_tc3h_p<BN, SB, ST, IN_PACKED>(a, h, slab_bytes, st) : launch_tc3h_p<BN, SB, ST, IN_F32>(a, h, slab_bytes, st);
 }
 
 }  // namespace
 
-static int slab_plan(const ConvArgs &a, int *R_out, int *rows_out)
+// Tile plan: R output rows per tile and the rows the slab must hold.  Two tilings: tiles that may straddle an image
+// boundary (every tile but the last is full; the slab needs KH - 1 extra rows per image it can touch) and tiles cut per
+// image (slab = R + KH - 1 rows, the last tile of an image may be short).  With N = 64 (two CTAs per SM, 113 KB each)
+// the smaller slab buys a third weight stage, which matters more than the few percent of idle GEMM rows: the weight
+// stage of k-block kb+1 can only be requested when k-block kb-1 retires, and its L2 latency (~1000 cycles) exceeds one
+// k-block of MMAs (448 cycles) -- with two stages every k-block waited for its weights.
+// n-tile width: 128 output channels per CTA (one CTA per SM) when N allows it, else 64 (two CTAs per SM).
+// ISS_B200_F16_BN=64 forces 64 everywhere (experiment: the slab fill / epilogue of one CTA then overlaps the other's main loop).
+static int f16_bn_for(int N)
+{
+    static const int forced = [] { const char *e = getenv("ISS_B200_F16_BN"); return e ? atoi(e) : 0; }();
+    if (forced == 64) return 64;
+    return N % 128 == 0 ? 128 : 64;
+}
+
+static int slab_plan(const ConvArgs &a, int *R_out, int *rows_out, int *tpi_out)
 {
     const int R = TBM / a.OW;
     const int cross = (R - 1) / a.OH + 1;
-    const int rows = R + (a.KH - 1) * (1 + cross);
+    int rows = R + (a.KH - 1) * (1 + cross);
+    int tpi = 0;
+    const int tiles_img = (a.OH + R - 1) / R;
+    const double eff_straddle = (double)(R * a.OW) / TBM, eff_img = (double)(a.OH * a.OW) / ((double)tiles_img * TBM);
+    if (f16_bn_for(a.N) == 64 && R <= a.OH && eff_img >= 0.92 * eff_straddle) { tpi = tiles_img; rows = R + a.KH - 1; }
     int slab_bytes = rows * a.W * a.C * 4;
-    if (slab_bytes < 32768) slab_bytes = 32768;
-    *R_out = R; *rows_out = rows;
+    if (slab_bytes < 32768) slab_bytes = 32768;                  // doubles as the 4 x 4 KB epilogue transpose buffers
+    *R_out = R; *rows_out = rows; *tpi_out = tpi;
     return slab_bytes;
 }
 
@@ -378,9 +462,9 @@ bool iss_conv_f16_slab_covers(const ConvArgs &a)
     if (!a.wt_f16 || a.SH != 1 || a.SW != 1 || a.PT != 0 || a.PL != 0 || a.KH * a.KW <= 1) return false;
     if (a.OH != a.H - a.KH + 1 || a.OW != a.W - a.KW + 1 || a.OW > TBM || a.Kp != a.K) return false;
     if (a.N % 64 != 0 || a.C % HBK != 0 || a.K % HBK != 0) return false;
-    int R, rows;
-    const int slab_bytes = slab_plan(a, &R, &rows);
-    if (a.N % 128 == 0) return TcHCfg<128, 2, 4>::FIXED + slab_bytes <= SMEM_CTA_MAX;
+    int R, rows, tpi;
+    const int slab_bytes = slab_plan(a, &R, &rows, &tpi);
+    if (f16_bn_for(a.N) == 128) return TcHCfg<128, 2, 4>::FIXED + slab_bytes <= SMEM_CTA_MAX;
     return TcHCfg<64, 3, 2>::FIXED + slab_bytes <= SMEM_CTA_MAX;
 }
 
@@ -388,12 +472,13 @@ bool iss_conv_f16_slab_covers(const ConvArgs &a)
 int iss_launch_conv_tc_f16(ConvArgs &a, cudaStream_t st)
 {
     if (!iss_conv_f16_slab_covers(a)) return 1;
-    int R, rows;
-    const int slab_bytes = slab_plan(a, &R, &rows);
+    int R, rows, tpi;
+    const int slab_bytes = slab_plan(a, &R, &rows, &tpi);
     a.slab_R = R;
+    a.slab_tpi = tpi;
     a.slab_rows = rows;
     a.in_elems = a.M / ((int64_t)a.OH * a.OW) * a.H * a.W * a.C;
-    const int BN = a.N % 128 == 0 ? 128 : 64;                   // same n-tiling as iss_prepare_f16_weights
+    const int BN = f16_bn_for(a.N);                              // same n-tiling as iss_prepare_f16_weights
     F16Args h{reinterpret_cast<const unsigned char *>(a.wt_f16), a.wt_f16_inv_scale};
     if (BN == 128) {
         if (TcHCfg<128, 4, 4>::FIXED + slab_bytes <= SMEM_CTA_MAX) return launch_tc3h<128, 4, 4>(a, h, slab_bytes, st);
@@ -418,7 +503,7 @@ int iss_prepare_f16_weights(const float *h_w, int K, int N, void **d_out, float 
     for (int k = 0; k < K; ++k)
         for (int n = 0; n < N; ++n) wt[(size_t)n * K + k] = h_w[(size_t)k * N + n];
     std::vector<__half> img;
-    const float scale = iss_f16_build_image(wt.data(), N, K, K, N % 128 == 0 ? 128 : 64, img);
+    const float scale = iss_f16_build_image(wt.data(), N, K, K, f16_bn_for(N), img);
     void *d = nullptr;
     cudaError_t e = cudaMalloc(&d, img.size() * sizeof(__half));
     if (e != cudaSuccess) { iss_set_error("cudaMalloc f16 weights: %s", cudaGetErrorString(e)); return ISS_ERR_NOMEM; }

@@ -256,6 +256,35 @@ def test_k2_all_gemm_engines_vs_oracle(rt, synth_models, mode):
         lib.iss_set_gemm_mode(prev)
 
 
+def test_k2_first_layer_fused_vs_standalone_and_fallback(rt, synth_models, monkeypatch):
+    """The first layer evaluated inside the second convolution's slab fill (float64 map Y, FirstFuse) against the
+    stand-alone first-layer kernel and the oracle; a batch whose patches are far apart must take the un-fused path
+    (the map would not fit) and still be right."""
+    from oracle import sidekit_oracle as sk
+    cfg, w = synth_models['smn']
+    sig = synth_audio(120, seed=5).astype(np.float32) / np.float32(32768)
+    mspec, loge = sk.logmel_loge(sig)
+    P = (len(loge) + 1) // 2
+    net = rt['engine'].CnnModel.from_keras(rt['ctx'], cfg, w, 21)
+    dm = torch.from_numpy(mspec).cuda()
+    lib = rt['lib'].load()
+    for ranges in ([(0, 700), (900, 1400)], [(3, 23), (P - 30, P)]):        # contiguous-ish (fused) / far apart (fallback)
+        ref = _oracle_probs(cfg, w, mspec, 21, ranges)
+        monkeypatch.setenv('ISS_B200_FUSE_FIRST', '1')
+        l0 = lib.iss_launch_count()
+        fused = net.forward(dm, ranges).cpu().numpy()
+        n_fused = lib.iss_launch_count() - l0
+        monkeypatch.setenv('ISS_B200_FUSE_FIRST', '0')
+        l0 = lib.iss_launch_count()
+        plain = net.forward(dm, ranges).cpu().numpy()
+        n_plain = lib.iss_launch_count() - l0
+        assert np.abs(fused - ref).max() <= 1e-4 and np.abs(plain - ref).max() <= 1e-4
+        assert np.abs(fused - plain).max() <= 2e-5
+        REPORT['k2_first_fused_%d_patches' % len(ref)] = dict(vs_oracle=float(np.abs(fused - ref).max()), vs_standalone=float(np.abs(fused - plain).max()),
+                                                              launches_fused=int(n_fused), launches_standalone=int(n_plain))
+    monkeypatch.delenv('ISS_B200_FUSE_FIRST', raising=False)
+
+
 @pytest.mark.parametrize('L', [68, 69, 70, 101, 135, 136])
 def test_k2_edge_replication(rt, synth_models, L):
     cfg, w = synth_models['sm']
