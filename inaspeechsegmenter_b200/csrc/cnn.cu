@@ -657,7 +657,7 @@ extern "C" int iss_cnn_forward(iss_ctx *ctx, iss_cnn *cnn, const float *d_mspec,
                 const char *fuse_env = getenv("ISS_B200_FUSE_FIRST");      // "0" = keep the stand-alone first-layer kernel (A/B tests)
                 const bool fuse_off = fuse_env && fuse_env[0] == '0';
                 if (li == 0 && direct && a.out_packed && !fuse_off && d_first_y && ranges_ascending && cnn->layers.size() > 1 &&
-                    cnn->layers[1].d.kind == ISS_LAYER_CONV2D && d.sh == 1 && d.sw == 1 && d.pad_top == 0 && d.pad_left == 0 &&
+                    cnn->layers[1].d.kind == ISS_LAYER_CONV2D && 128 % (d.cout / 4) == 0 && d.sh == 1 && d.sw == 1 && d.pad_top == 0 && d.pad_left == 0 &&
                     d.pad_bottom == 0 && d.pad_right == 0 && !(d.flags & ISS_F_SOFTMAX)) {
                     const int64_t f_first = host_row0(b0), f_last = host_row0(b0 + nb - 1);
                     const int64_t rows = f_last - f_first + Lr.out_h;

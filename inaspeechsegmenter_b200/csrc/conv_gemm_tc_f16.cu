@@ -159,6 +159,8 @@ conv_gemm_tc3h_kernel(const ConvArgs a, const F16Args h, const FirstFuse ff)
             int p = tid / cpp, j = tid - p * cpp;
             const int dp = 128 / cpp, dj = 128 - dp * cpp;
             if constexpr (MODE == IN_FIRST) {
+                // 128 % cpp == 0 (checked by the launcher): a thread keeps its 4 channels (chunk jc) for the whole fill,
+                // so the per-channel constants live in registers and the pixel walk needs no division
                 // per-image constants of the (at most 4) patches this slab touches: {mu, 1 / sigma} in float64, Y row of its row 0
                 double *tabd = reinterpret_cast<double *>(bars + 2 * ST + 2 * SB + 2);         // [4][2]
                 int64_t *tabr = reinterpret_cast<int64_t *>(tabd + 8);                           // [4]
@@ -175,40 +177,59 @@ conv_gemm_tc3h_kernel(const ConvArgs a, const F16Args h, const FirstFuse ff)
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 const int f_flags = ff.flags;
+                const int jc = tid % cpp, pstep = 128 / cpp;
+                double Sc[4];
+                float eb[4], es1[4], et1[4], es2[4], et2[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int c = jc * 4 + e;
+                    Sc[e] = ff.S[c];
+                    eb[e] = (f_flags & ISS_F_BIAS) ? ff.bias[c] : 0.f;
+                    es1[e] = (f_flags & ISS_F_AFFINE_PRE) ? ff.pre_scale[c] : 1.f;  et1[e] = (f_flags & ISS_F_AFFINE_PRE) ? ff.pre_shift[c] : 0.f;
+                    es2[e] = (f_flags & ISS_F_AFFINE_POST) ? ff.post_scale[c] : 1.f; et2[e] = (f_flags & ISS_F_AFFINE_POST) ? ff.post_shift[c] : 0.f;
+                }
                 const int row_len = a.W * a.C;                   // doubles per Y row
-                for (int q = tid; q < total; q += 128) {
-                    const uint32_t dst = slab_u32 + (uint32_t)p * pix_bytes + (uint32_t)(((j & ~7) | ((j ^ p) & 7)) << 4);
-                    const int srow = p / a.W, x = p - srow * a.W;
-                    const int64_t g = g0 + srow;                  // input row in the global (image-major) row sequence
-                    const int64_t img = g / a.H;
-                    const int ih = (int)(g - img * a.H);
-                    const int ti = (int)(img - img0);
+                // pixel pp = tid / cpp + i * pstep of the slab  <->  (image ti relative to img0, input row ih, column x)
+                int pp = tid / cpp;
+                int x = pp % a.W, srow = pp / a.W;
+                const int64_t gfirst = g0 + srow;
+                int ti = (int)(gfirst / a.H - img0);
+                int ih = (int)(gfirst - (gfirst / a.H) * a.H);
+                const int npix = rows * a.W;
+                for (; pp < npix; pp += pstep) {
+                    const uint32_t dst = slab_u32 + (uint32_t)pp * pix_bytes + (uint32_t)(((jc & ~7) | ((jc ^ pp) & 7)) << 4);
                     uint4 wd = make_uint4(0u, 0u, 0u, 0u);
                     if (ti < 4 && tabr[ti] >= 0) {
                         const double mu = tabd[2 * ti], inv = tabd[2 * ti + 1];
-                        const double *yp = ff.Y + (tabr[ti] + ih) * (int64_t)row_len + (int64_t)x * a.C + j * 4;
+                        const double *yp = ff.Y + (tabr[ti] + ih) * (int64_t)row_len + x * a.C + jc * 4;
                         const double2 y01 = __ldg(reinterpret_cast<const double2 *>(yp));
                         const double2 y23 = __ldg(reinterpret_cast<const double2 *>(yp) + 1);
                         const double yv[4] = {y01.x, y01.y, y23.x, y23.y};
                         uint32_t w4[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            const int c = j * 4 + e;
-                            float v = (float)((yv[e] - mu * __ldg(ff.S + c)) * inv);
-                            if (f_flags & ISS_F_BIAS) v += __ldg(ff.bias + c);
-                            if (f_flags & ISS_F_AFFINE_PRE) v = fmaf(v, __ldg(ff.pre_scale + c), __ldg(ff.pre_shift + c));
+                            float v = (float)((yv[e] - mu * Sc[e]) * inv) + eb[e];
+                            if (f_flags & ISS_F_AFFINE_PRE) v = fmaf(v, es1[e], et1[e]);
                             if (f_flags & ISS_F_RELU) v = fmaxf(v, 0.f);
                             if (f_flags & ISS_F_SIGMOID) v = 1.f / (1.f + expf(-v));
-                            if (f_flags & ISS_F_AFFINE_POST) v = fmaf(v, __ldg(ff.post_scale + c), __ldg(ff.post_shift + c));
+                            if (f_flags & ISS_F_AFFINE_POST) v = fmaf(v, es2[e], et2[e]);
                             w4[e] = iss_pack_split(v);
                         }
                         wd = make_uint4(w4[0], w4[1], w4[2], w4[3]);
                     }
                     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(wd.x), "r"(wd.y), "r"(wd.z), "r"(wd.w) : "memory");
+                    x += pstep;
+                    while (x >= a.W) { x -= a.W; if (++ih == a.H) { ih = 0; ++ti; } }
+                }
+            } else {
+                for (int q = tid; q < total; q += 128) {
+                    const uint32_t dst = slab_u32 + (uint32_t)p * pix_bytes + (uint32_t)(((j & ~7) | ((j ^ p) & 7)) << 4);
+                    const bool ok = q < avail;
+                    cp_async16_u32(dst, src0 + (ok ? (size_t)q * 4 : 0), ok ? 16 : 0);
                     p += dp; j += dj;
                     if (j >= cpp) { j -= cpp; ++p; }
                 }
-            } else
+            }
             cp_async_commit();
             cp_async_wait<0>();
             asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -419,7 +440,10 @@ int launch_tc3h_p(const ConvArgs &a, const F16Args &h, int slab_bytes, cudaStrea
 template <int BN, int SB, int ST>
 int launch_tc3h(const ConvArgs &a, const F16Args &h, int slab_bytes, cudaStream_t st)
 {
-    if (a.first) return launch_tc3h_p<BN, SB, ST, IN_FIRST>(a, h, slab_bytes, st);
+    if (a.first) {
+        ISS_REQUIRE(128 % (a.C / 4) == 0, ISS_ERR_UNSUPPORTED, "conv_tc_f16: fused first layer needs 128 %% (C / 4) == 0");
+        return launch_tc3h_p<BN, SB, ST, IN_FIRST>(a, h, slab_bytes, st);
+    }
     return a.in_packed ? launch_tc3h_p<BN, SB, ST, IN_PACKED>(a, h, slab_bytes, st) : launch_tc3h_p<BN, SB, ST, IN_F32>(a, h, slab_bytes, st);
 }
 
@@ -448,7 +472,8 @@ static int slab_plan(const ConvArgs &a, int *R_out, int *rows_out, int *tpi_out)
     int tpi = 0;
     const int tiles_img = (a.OH + R - 1) / R;
     const double eff_straddle = (double)(R * a.OW) / TBM, eff_img = (double)(a.OH * a.OW) / ((double)tiles_img * TBM);
-    if (f16_bn_for(a.N) == 64 && R <= a.OH && eff_img >= 0.92 * eff_straddle) { tpi = tiles_img; rows = R + a.KH - 1; }
+    static const bool tpi_off = [] { const char *e = getenv("ISS_B200_F16_TPI"); return e && e[0] == '0'; }();   // A/B experiments
+    if (!tpi_off && f16_bn_for(a.N) == 64 && R <= a.OH && eff_img >= 0.92 * eff_straddle) { tpi = tiles_img; rows = R + a.KH - 1; }
     int slab_bytes = rows * a.W * a.C * 4;
     if (slab_bytes < 32768) slab_bytes = 32768;                  // doubles as the 4 x 4 KB epilogue transpose buffers
     *R_out = R; *rows_out = rows; *tpi_out = tpi;

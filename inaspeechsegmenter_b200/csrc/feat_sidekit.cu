@@ -10,8 +10,10 @@
 // exactly once with 16-byte vector loads and staged in shared memory together
 // with the Hann window, the FFT twiddles and the sparse mel filterbank.  Each warp
 // then processes frames independently: a 512-point real FFT is computed as a
-// 256-point complex radix-4 Stockham FFT (4 passes through a per-warp shared
-// buffer, SoA + skewed to avoid bank conflicts) followed by the even/odd split.
+// 256-point complex FFT held in registers (8 points per lane, ONE conflict-free
+// transpose through shared memory + two rounds of shuffles: fft256r.cuh) followed
+// by the even/odd split.  (Round 1 used a 4-pass radix-4 Stockham FFT through shared
+// memory; with float64 data that was shared-memory bound: 33 % conflict wavefronts.)
 // T = float: fast path; T = double: window/FFT/power in fp64 then rounded to f32,
 // which is the reference's own precision recipe (sidekit_mfcc.py:231-233).
 #include <math.h>
@@ -22,7 +24,7 @@
 
 namespace {
 
-#include "fft256.cuh"
+#include "fft256r.cuh"
 
 
 constexpr int FR = 48;                               // frames per CTA tile (int16 staging + 48 frames => 3 CTAs/SM in fp64 mode)
@@ -51,12 +53,12 @@ struct Smem {
     // staged verbatim: int16 PCM stays 2 bytes/sample in shared memory and is scaled by 1/32768 on use
     typename std::conditional<PCM == ISS_PCM_S16, int16_t, float>::type samples[TILE_SAMPLES + 8];
     T win[ISS_WIN];
-    T tw256[512];
+    Cplx<T> twA[7 * 32];                    // W256^(lane * k1), k1 = 1..7 (fft256r.cuh)
+    Cplx<T> twB[7 * 4];                     // W32^(r * k2a),   k2a = 1..7
     T tw512[2 * 257 + 2];
     float fbw[ISS_FB_MAXNNZ];
     int fb_lo[ISS_NMEL], fb_cnt[ISS_NMEL], fb_off[ISS_NMEL];
-    T re[NWARP][ZPAD];
-    T im[NWARP][ZPAD];
+    Cplx<T> buf[NWARP][FFT_BUF];            // per-warp transpose rows, then the spectrum Z[k] at k + 2 (k >> 6)
     float pw[NWARP][ZPAD];
     double red[NWARP][2];
 };
@@ -77,7 +79,14 @@ sidekit_features_kernel(const void *__restrict__ pcm, int64_t n_samples, int64_t
 
     // ---- stage tables (L2-resident, tiny) and the tile's samples (HBM, once) ----
     for (int i = tid; i < ISS_WIN; i += NTHREAD) S.win[i] = Tab<T>::win(tabs)[i];
-    for (int i = tid; i < 512; i += NTHREAD) S.tw256[i] = Tab<T>::tw256(tabs)[i];
+    for (int i = tid; i < 7 * 32; i += NTHREAD) {                // W256^(l * k1) = tw256[l * k1]  (cos, -sin)
+        const int k1 = i / 32 + 1, l = i % 32;
+        S.twA[i].x = Tab<T>::tw256(tabs)[2 * (l * k1)]; S.twA[i].y = Tab<T>::tw256(tabs)[2 * (l * k1) + 1];
+    }
+    if (tid < 7 * 4) {                                           // W32^(r * k) = tw256[8 * r * k]
+        const int k = tid / 4 + 1, r = tid % 4;
+        S.twB[tid].x = Tab<T>::tw256(tabs)[2 * (8 * r * k)]; S.twB[tid].y = Tab<T>::tw256(tabs)[2 * (8 * r * k) + 1];
+    }
     for (int i = tid; i < 2 * 257; i += NTHREAD) S.tw512[i] = Tab<T>::tw512(tabs)[i];
     for (int i = tid; i < tabs->nnz; i += NTHREAD) S.fbw[i] = tabs->w[i];
     if (tid < ISS_NMEL) { S.fb_lo[tid] = tabs->lo[tid]; S.fb_cnt[tid] = tabs->cnt[tid]; S.fb_off[tid] = tabs->off[tid]; }
@@ -109,47 +118,59 @@ sidekit_features_kernel(const void *__restrict__ pcm, int64_t n_samples, int64_t
     }
     __syncthreads();
 
-    T *re = S.re[warp], *im = S.im[warp];
+    Cplx<T> *buf = S.buf[warp];
     float *pw = S.pw[warp];
     double acc_sum = 0.0, acc_cnt = 0.0;
+    const int zk1 = lane >> 2, zk2b = ((lane & 1) << 1) | ((lane >> 1) & 1);   // where this lane's FFT outputs belong
 
     for (int fl = warp; fl < nfr; fl += NWARP) {
         const auto *xs = S.samples + fl * ISS_HOP;
         auto x = [&](int n) -> float {
             return (PCM == ISS_PCM_S16) ? (float)xs[n] * (1.0f / 32768.0f) : (float)xs[n];
         };
-        // ---- pre-emphasis (f32, numpy op order: x - (x_prev * 0.97f)), energy, window ----
+        // ---- pre-emphasis (f32, numpy op order: x - (x_prev * 0.97f)), energy, window; the 512-point real
+        //      frame is packed as z[m] = v[2m] + i v[2m+1] and lane l keeps z[32 n1 + l], n1 = 0..7, in registers ----
+        T zr[8], zi[8];
         double e = 0.0;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int n = lane + 32 * i;                 // 0..511
-            T v = (T)0;
+        for (int n1 = 0; n1 < 8; ++n1) {
+            const int n = 64 * n1 + 2 * lane;            // even sample of z[32 n1 + lane]; ISS_WIN is even
+            T v0 = (T)0, v1 = (T)0;
             if (n < ISS_WIN) {
-                const float xc = x(n);
-                const float xp = (n == 0) ? xc : x(n - 1);
-                const float y = __fsub_rn(xc, __fmul_rn(xp, 0.97f));
-                e += (double)y * (double)y;
-                v = (T)y * S.win[n];
+                const float xa = x(n), xb = x(n + 1);
+                const float xp = (n == 0) ? xa : x(n - 1);
+                const float y0 = __fsub_rn(xa, __fmul_rn(xp, 0.97f));
+                const float y1 = __fsub_rn(xb, __fmul_rn(xa, 0.97f));
+                e += (double)y0 * (double)y0;
+                e += (double)y1 * (double)y1;
+                v0 = (T)y0 * S.win[n];
+                v1 = (T)y1 * S.win[n + 1];
             }
-            // z[m] = v[2m] + i v[2m+1]
-            if (n & 1) im[skewT<T>(n >> 1)] = v; else re[skewT<T>(n >> 1)] = v;
+            zr[n1] = v0; zi[n1] = v1;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+
+        warp_fft256_reg<T>(zr, zi, buf, S.twA, S.twB, lane);
+
+        // ---- spectrum to shared memory (Z[k] at k + 2 (k >> 6): conflict-free 16-byte stores), then the split
+        //      X[k] = E[k] + W512^k O[k], power -> f32 ----
+#pragma unroll
+        for (int k2a = 0; k2a < 8; ++k2a) {
+            Cplx<T> v; v.x = zr[k2a]; v.y = zi[k2a];
+            buf[zk1 + 8 * k2a + 64 * zk2b + 2 * zk2b] = v;
+        }
         __syncwarp();
-
-        warp_fft256<T>(re, im, S.tw256, lane);
-
-        // ---- split the packed spectrum: X[k] = E[k] + W512^k O[k], power -> f32 ----
 #pragma unroll
         for (int i = 0; i < 9; ++i) {
             const int k = lane + 32 * i;
             if (k <= 256) {
-                const int ka = skewT<T>(k & 255), kb = skewT<T>((256 - k) & 255);
-                const T zr = re[ka], zi = im[ka];
-                const T cr = re[kb], ci = -im[kb];                  // conj(Z[256-k])
-                const T er = (T)0.5 * (zr + cr), ei = (T)0.5 * (zi + ci);
-                const T dr = (T)0.5 * (zr - cr), di = (T)0.5 * (zi - ci);
+                const int ka = k & 255, kb = (256 - k) & 255;
+                const Cplx<T> za = buf[ka + 2 * (ka >> 6)], zb = buf[kb + 2 * (kb >> 6)];
+                const T zr_ = za.x, zi_ = za.y;
+                const T cr = zb.x, ci = -zb.y;                      // conj(Z[256-k])
+                const T er = (T)0.5 * (zr_ + cr), ei = (T)0.5 * (zi_ + ci);
+                const T dr = (T)0.5 * (zr_ - cr), di = (T)0.5 * (zi_ - ci);
                 const T orr = di, oi = -dr;                          // O = -i * (Z - conj)/2
                 const T c = S.tw512[2 * k], sn = S.tw512[2 * k + 1];
                 const T xr = er + (orr * c - oi * sn);

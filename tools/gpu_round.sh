@@ -9,6 +9,8 @@ mkdir -p gpurun_out
   timeout 200 python tools/tc_check.py 0 10 | grep -E "^mode"
   echo "== default"; timeout 200 python tools/tc_check.py 3 10 | grep -E "^mode|rror"
   echo "== ISS_B200_FUSE_FIRST=0"; ISS_B200_FUSE_FIRST=0 timeout 200 python tools/tc_check.py 3 10 | grep -E "^mode|rror"
+  echo "== ISS_B200_F16_TPI=0"; ISS_B200_F16_TPI=0 timeout 200 python tools/tc_check.py 3 10 | grep -E "^mode|rror"
+  echo "== ISS_B200_F16_TPI=0 ISS_B200_FUSE_FIRST=0"; ISS_B200_F16_TPI=0 ISS_B200_FUSE_FIRST=0 timeout 200 python tools/tc_check.py 3 10 | grep -E "^mode|rror"
   echo "== ISS_B200_F16_BN=64"; ISS_B200_F16_BN=64 timeout 200 python tools/tc_check.py 3 10 | grep -E "^mode|rror"
 } > gpurun_out/${TAG}_ab.log 2>&1
 if [ "$MODE" = full ]; then
