@@ -428,7 +428,7 @@ extern "C" int iss_cnn_create(iss_ctx *ctx, const iss_layer_desc *layers, int n_
         if (C % 32 != 0 || K % 32 != 0 || d.cout % 32 != 0) continue;
         int rc = iss_prepare_tc_weights(h_blob + d.w_off, K, d.cout, &L.d_wt, &L.Kp);
         if (rc != ISS_OK) { iss_cnn_destroy(m); return rc; }
-        if (d.kind == ISS_LAYER_CONV2D && d.kh * d.kw > 1 && d.cin % 64 == 0) {
+        if (d.cin % 64 == 0) {                                    // fp16-split engine (slab or gather kernel)
             rc = iss_prepare_f16_weights(h_blob + d.w_off, K, d.cout, &L.d_wt_f16, &L.f16_inv_scale);
             if (rc != ISS_OK) { iss_cnn_destroy(m); return rc; }
         }
@@ -508,6 +508,17 @@ void fill_conv_args(const Layer &Lr, int64_t nb, ConvArgs &a)
     }
 }
 
+// Will this Conv2D / Dense layer run on the fp16-split engine (slab kernel for un-padded stride-1 KHxKW convolutions,
+// gather kernel for everything else it has a weight image for)?  Only those kernels read / write split-half words.
+bool f16_engine_covers(const Layer &L, const ConvArgs &a)
+{
+    if (L.d.kind == ISS_LAYER_MAXPOOL) return false;
+    if (L.d.kind == ISS_LAYER_CONV2D && L.d.pad_bottom == 0 && L.d.pad_right == 0 && iss_conv_f16_slab_covers(a)) return true;
+    // the gather kernel takes symmetric padding only through PT / PL + the bounds check: 'same' padding with an extra
+    // bottom / right row is covered too (rows past the input are zero-filled)
+    return iss_conv_f16_gather_covers(a);
+}
+
 // Should the tensor produced by layer `li` be stored as split-half words?  Yes iff the next compute layer
 // (pooling layers in between keep the format) is a convolution the fp16-split slab kernel takes.
 bool wants_packed_output(const iss_cnn *cnn, size_t li, int64_t nb)
@@ -518,12 +529,11 @@ bool wants_packed_output(const iss_cnn *cnn, size_t li, int64_t nb)
         if (cnn->layers[j].in_c % 4 != 0) return false;          // the packed pooling kernel moves 4 channels per thread
         ++j;
     }
-    if (j >= cnn->layers.size() || cnn->layers[j].d.kind != ISS_LAYER_CONV2D) return false;
+    if (j >= cnn->layers.size()) return false;
     const Layer &Nx = cnn->layers[j];
-    if (Nx.d.pad_bottom != 0 || Nx.d.pad_right != 0) return false;
     ConvArgs probe = {};
     fill_conv_args(Nx, nb, probe);
-    return iss_conv_f16_slab_covers(probe);
+    return f16_engine_covers(Nx, probe);
 }
 
 }  // namespace
@@ -646,9 +656,9 @@ extern "C" int iss_cnn_forward(iss_ctx *ctx, iss_cnn *cnn, const float *d_mspec,
                 const bool direct = li == 0 && d.kind == ISS_LAYER_CONV2D && d.cin == 1 &&
                                     (d.cout == 16 || d.cout == 32 || d.cout == 64 || d.cout == 128) && !(d.flags & ISS_F_SOFTMAX);
                 // only the direct first-layer kernel and the fp16-split slab kernel can emit split-half words
-                const bool can_pack = direct || (li > 0 && iss_get_gemm_mode() == ISS_GEMM_TC_F16 && iss_conv_f16_slab_covers(a));
+                const bool can_pack = direct || (li > 0 && iss_get_gemm_mode() == ISS_GEMM_TC_F16 && f16_engine_covers(Lr, a));
                 a.out_packed = (!last && can_pack && wants_packed_output(cnn, li, nb)) ? 1 : 0;
-                ISS_REQUIRE(!a.in_packed || (li > 0 && iss_conv_f16_slab_covers(a)), ISS_ERR_UNSUPPORTED,
+                ISS_REQUIRE(!a.in_packed || (li > 0 && f16_engine_covers(Lr, a)), ISS_ERR_UNSUPPORTED,
                             "iss_cnn_forward: layer %d was handed split-half words it cannot read", (int)li);
                 int rc;
                 // Fold the first layer into the next convolution's slab fill (FirstFuse, conv_gemm.cuh)?  Needs: the direct
@@ -656,8 +666,14 @@ extern "C" int iss_cnn_forward(iss_ctx *ctx, iss_cnn *cnn, const float *d_mspec,
                 // whose patches span few enough frames for the float64 map.
                 const char *fuse_env = getenv("ISS_B200_FUSE_FIRST");      // "0" = keep the stand-alone first-layer kernel (A/B tests)
                 const bool fuse_off = fuse_env && fuse_env[0] == '0';
-                if (li == 0 && direct && a.out_packed && !fuse_off && d_first_y && ranges_ascending && cnn->layers.size() > 1 &&
-                    cnn->layers[1].d.kind == ISS_LAYER_CONV2D && 128 % (d.cout / 4) == 0 && d.sh == 1 && d.sw == 1 && d.pad_top == 0 && d.pad_left == 0 &&
+                bool next_is_slab = false;                       // the FIRST mode lives in the slab kernel only
+                if (li == 0 && cnn->layers.size() > 1 && cnn->layers[1].d.kind == ISS_LAYER_CONV2D &&
+                    cnn->layers[1].d.pad_bottom == 0 && cnn->layers[1].d.pad_right == 0) {
+                    ConvArgs p1 = {};
+                    fill_conv_args(cnn->layers[1], nb, p1);
+                    next_is_slab = iss_conv_f16_slab_covers(p1);
+                }
+                if (li == 0 && direct && a.out_packed && !fuse_off && d_first_y && ranges_ascending && next_is_slab && 128 % (d.cout / 4) == 0 && d.sh == 1 && d.sw == 1 && d.pad_top == 0 && d.pad_left == 0 &&
                     d.pad_bottom == 0 && d.pad_right == 0 && !(d.flags & ISS_F_SOFTMAX)) {
                     const int64_t f_first = host_row0(b0), f_last = host_row0(b0 + nb - 1);
                     const int64_t rows = f_last - f_first + Lr.out_h;

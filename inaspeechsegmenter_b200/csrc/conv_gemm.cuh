@@ -60,6 +60,7 @@ struct ConvArgs {
     const void *wt_f16; float wt_f16_inv_scale;
     // activation formats of that engine: fp32 values (0) or split-half words lo16 << 16 | hi16 (1)
     int in_packed, out_packed;
+    int residual_packed;    // `residual` holds split-half words (fp16-split kernels only)
     const FirstFuse *first;         // host pointer, non-null: FIRST mode (copied into the kernel parameters)
     // slab kernel (conv_gemm_tc_f16.cu) only, filled in by iss_launch_conv_tc_f16
     int slab_R;             // output rows (of width OW) per 128-row GEMM tile
@@ -84,6 +85,10 @@ int iss_prepare_tc_weights(const float *h_w, int K, int N, float **d_out, int *K
 int iss_prepare_f16_weights(const float *h_w, int K, int N, void **d_out, float *inv_scale);
 // does engine 3's slab kernel cover this layer (geometry + prepared image + shared memory)?
 bool iss_conv_f16_slab_covers(const ConvArgs &a);
+// does engine 3's gather kernel (conv_gemm_tc_f16g.cu: any stride / padding / 1x1) cover this layer?
+bool iss_conv_f16_gather_covers(const ConvArgs &a);
+// n-tile width of engine 3 for N output channels (must agree between the weight image and the launch)
+int iss_f16_bn_for(int N);
 
 // Launches the layer on `st`.  first = gather from log-mel rows with (x - mu) / sigma.
 int iss_launch_conv(const ConvArgs &a, bool first, cudaStream_t st);

@@ -360,6 +360,7 @@ extern "C" int iss_get_gemm_mode(void)
 }
 
 int iss_launch_conv_tc_f16(ConvArgs &a, cudaStream_t st);              // conv_gemm_tc_f16.cu; 1 = layer not covered
+int iss_launch_conv_tc_f16g(const ConvArgs &a, cudaStream_t st);       // conv_gemm_tc_f16g.cu; 1 = layer not covered
 
 bool iss_conv_tc_eligible(const ConvArgs &a)
 {
@@ -369,10 +370,16 @@ bool iss_conv_tc_eligible(const ConvArgs &a)
 int iss_launch_conv_tc(const ConvArgs &a_in, int mode, cudaStream_t st)
 {
     ConvArgs a = a_in;
-    if (mode == ISS_GEMM_TC_F16) {                                      // fp16-split slab kernel where it applies
-        const int rc = iss_launch_conv_tc_f16(a, st);
+    if (mode == ISS_GEMM_TC_F16) {                                      // fp16-split kernels where they apply: slab, then gather
+        int rc = iss_launch_conv_tc_f16(a, st);
         if (rc != 1) return rc;
+        static const bool gather_off = [] { const char *e = getenv("ISS_B200_F16_GATHER"); return e && e[0] == '0'; }();   // A/B experiments
+        if (!gather_off || a.in_packed || a.out_packed || a.residual_packed) {
+            rc = iss_launch_conv_tc_f16g(a, st);
+            if (rc != 1) return rc;
+        }
     }
+    ISS_REQUIRE(!a.in_packed && !a.out_packed && !a.residual_packed, ISS_ERR_UNSUPPORTED, "conv_tc: split-half tensors need the fp16-split engine");
     // two accumulators per tile (main + correction) => BN <= 128 (2 x 128 + A ring <= 512 TMEM columns)
     if (a.N % 128 == 0) return launch_tc2<128, 4, 4, 4>(a, st);          // 193 KB smem, 512 TMEM cols (2x128 acc + 4 A stages), 1 CTA/SM
     if (a.N % 64 == 0) return launch_tc2<64, 3, 3, 2>(a, st);            //  97 KB smem, 256 TMEM cols, 2 CTAs/SM

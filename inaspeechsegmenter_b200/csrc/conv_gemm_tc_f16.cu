@@ -30,6 +30,7 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <type_traits>
 #include <vector>
 
 #include "f16_image.cuh"
@@ -190,36 +191,57 @@ conv_gemm_tc3h_kernel(const ConvArgs a, const F16Args h, const FirstFuse ff)
                 }
                 const int row_len = a.W * a.C;                   // doubles per Y row
                 // pixel pp = tid / cpp + i * pstep of the slab  <->  (image ti relative to img0, input row ih, column x)
+                // The map Y lives in L2 (shared by ~33 overlapping patches): a dependent load per pixel would serialise
+                // 28 x ~800 cycles of L2 latency per tile, so the loads of FB pixels are issued before any is consumed.
+                constexpr int FB = 8;
                 int pp = tid / cpp;
                 int x = pp % a.W, srow = pp / a.W;
                 const int64_t gfirst = g0 + srow;
                 int ti = (int)(gfirst / a.H - img0);
                 int ih = (int)(gfirst - (gfirst / a.H) * a.H);
                 const int npix = rows * a.W;
-                for (; pp < npix; pp += pstep) {
-                    const uint32_t dst = slab_u32 + (uint32_t)pp * pix_bytes + (uint32_t)(((jc & ~7) | ((jc ^ pp) & 7)) << 4);
-                    uint4 wd = make_uint4(0u, 0u, 0u, 0u);
-                    if (ti < 4 && tabr[ti] >= 0) {
-                        const double mu = tabd[2 * ti], inv = tabd[2 * ti + 1];
-                        const double *yp = ff.Y + (tabr[ti] + ih) * (int64_t)row_len + x * a.C + jc * 4;
-                        const double2 y01 = __ldg(reinterpret_cast<const double2 *>(yp));
-                        const double2 y23 = __ldg(reinterpret_cast<const double2 *>(yp) + 1);
-                        const double yv[4] = {y01.x, y01.y, y23.x, y23.y};
-                        uint32_t w4[4];
+                while (pp < npix) {
+                    double2 ya[FB], yb[FB];
+                    uint32_t dsts[FB];
+                    int tis[FB];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            float v = (float)((yv[e] - mu * Sc[e]) * inv) + eb[e];
-                            if (f_flags & ISS_F_AFFINE_PRE) v = fmaf(v, es1[e], et1[e]);
-                            if (f_flags & ISS_F_RELU) v = fmaxf(v, 0.f);
-                            if (f_flags & ISS_F_SIGMOID) v = 1.f / (1.f + expf(-v));
-                            if (f_flags & ISS_F_AFFINE_POST) v = fmaf(v, es2[e], et2[e]);
-                            w4[e] = iss_pack_split(v);
+                    for (int f = 0; f < FB; ++f) {
+                        tis[f] = -1;
+                        dsts[f] = 0;
+                        if (pp < npix) {
+                            dsts[f] = slab_u32 + (uint32_t)pp * pix_bytes + (uint32_t)(((jc & ~7) | ((jc ^ pp) & 7)) << 4);
+                            tis[f] = 4;                          // 4 = zero fill
+                            if (ti < 4 && tabr[ti] >= 0) {
+                                tis[f] = ti;
+                                const double *yp = ff.Y + (tabr[ti] + ih) * (int64_t)row_len + x * a.C + jc * 4;
+                                ya[f] = __ldg(reinterpret_cast<const double2 *>(yp));
+                                yb[f] = __ldg(reinterpret_cast<const double2 *>(yp) + 1);
+                            }
+                            pp += pstep; x += pstep;
+                            while (x >= a.W) { x -= a.W; if (++ih == a.H) { ih = 0; ++ti; } }
                         }
-                        wd = make_uint4(w4[0], w4[1], w4[2], w4[3]);
                     }
-                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(wd.x), "r"(wd.y), "r"(wd.z), "r"(wd.w) : "memory");
-                    x += pstep;
-                    while (x >= a.W) { x -= a.W; if (++ih == a.H) { ih = 0; ++ti; } }
+#pragma unroll
+                    for (int f = 0; f < FB; ++f) {
+                        if (tis[f] < 0) continue;
+                        uint4 wd = make_uint4(0u, 0u, 0u, 0u);
+                        if (tis[f] < 4) {
+                            const double mu = tabd[2 * tis[f]], inv = tabd[2 * tis[f] + 1];
+                            const double yv[4] = {ya[f].x, ya[f].y, yb[f].x, yb[f].y};
+                            uint32_t w4[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                float v = (float)((yv[e] - mu * Sc[e]) * inv) + eb[e];
+                                if (f_flags & ISS_F_AFFINE_PRE) v = fmaf(v, es1[e], et1[e]);
+                                if (f_flags & ISS_F_RELU) v = fmaxf(v, 0.f);
+                                if (f_flags & ISS_F_SIGMOID) v = 1.f / (1.f + expf(-v));
+                                if (f_flags & ISS_F_AFFINE_POST) v = fmaf(v, es2[e], et2[e]);
+                                w4[e] = iss_pack_split(v);
+                            }
+                            wd = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                        }
+                        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dsts[f]), "r"(wd.x), "r"(wd.y), "r"(wd.z), "r"(wd.w) : "memory");
+                    }
                 }
             } else {
                 for (int q = tid; q < total; q += 128) {
@@ -302,6 +324,9 @@ conv_gemm_tc3h_kernel(const ConvArgs a, const F16Args h, const FirstFuse ff)
         }
 
         // ============================ epilogue ============================
+        // (28 % of a CTA's life in the first version: fully unrolled 1700-instruction body -> instruction-cache misses, two
+        // store paths per position.)  Bias + BatchNorm affine are folded into one FMA per value (inv_scale is a power of two),
+        // the output format is a template of the store lambda, the row loop is unrolled by 2 only.
         if (lane == 0) mbar_wait(accum, 0, 5);
         __syncwarp();
         tc_fence_after();
@@ -312,54 +337,60 @@ conv_gemm_tc3h_kernel(const ConvArgs a, const F16Args h, const FirstFuse ff)
         const float inv_s = h.inv_scale;
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
-            uint32_t acc[32];
             {
-                uint32_t corr[32];
+                uint32_t acc[32], corr[32];
                 tmem_ld32(tmem_base + lane_addr + c, acc);
                 tmem_ld32(tmem_base + lane_addr + BN + c, corr);
+                __syncwarp();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint((__uint_as_float(acc[j]) + __uint_as_float(corr[j])) * inv_s);
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4 *>(stage_buf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                        make_float4(__uint_as_float(acc[4 * j]) + __uint_as_float(corr[4 * j]), __uint_as_float(acc[4 * j + 1]) + __uint_as_float(corr[4 * j + 1]),
+                                    __uint_as_float(acc[4 * j + 2]) + __uint_as_float(corr[4 * j + 2]), __uint_as_float(acc[4 * j + 3]) + __uint_as_float(corr[4 * j + 3]));
             }
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                *reinterpret_cast<uint4 *>(stage_buf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-                    make_uint4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
             __syncwarp();
             const int nb = n0 + c + chunk * 4;
-            float eb[4], es1[4], et1[4], es2[4], et2[4];
+            float k1[4], k0[4], es2[4], et2[4];                  // y = acc * k1 + k0  ==  ((acc * inv_s) + bias) * pre_scale + pre_shift
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                eb[q] = has_bias ? __ldg(a.bias + nb + q) : 0.f;
-                es1[q] = pre ? __ldg(a.pre_scale + nb + q) : 1.f;  et1[q] = pre ? __ldg(a.pre_shift + nb + q) : 0.f;
+                const float eb = has_bias ? __ldg(a.bias + nb + q) : 0.f;
+                const float s1 = pre ? __ldg(a.pre_scale + nb + q) : 1.f, t1 = pre ? __ldg(a.pre_shift + nb + q) : 0.f;
+                k1[q] = inv_s * s1; k0[q] = fmaf(eb, s1, t1);
                 es2[q] = post ? __ldg(a.post_scale + nb + q) : 1.f; et2[q] = post ? __ldg(a.post_shift + nb + q) : 0.f;
             }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int rl = 4 * i + sub;
-                const int rr = quad * 32 + rl;
-                const int64_t m = mbase + rr;
-                const uint4 q4 = *reinterpret_cast<const uint4 *>(stage_buf + rl * 128 + ((chunk ^ (rl & 7)) << 4));
-                if (rr < valid) {
-                    float y[4] = {__uint_as_float(q4.x), __uint_as_float(q4.y), __uint_as_float(q4.z), __uint_as_float(q4.w)};
-                    float4 rs = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (resid) rs = __ldg(reinterpret_cast<const float4 *>(a.residual + m * a.N + nb));
-                    const float rv[4] = {rs.x, rs.y, rs.z, rs.w};
+            auto rows = [&](auto packed_tag, auto resid_tag) {
+                constexpr bool OUT_PACKED = decltype(packed_tag)::value, RESID = decltype(resid_tag)::value;
+#pragma unroll 2
+                for (int i = 0; i < 8; ++i) {
+                    const int rl = 4 * i + sub;
+                    const int rr = quad * 32 + rl;
+                    if (rr >= valid) continue;
+                    const float4 q4 = *reinterpret_cast<const float4 *>(stage_buf + rl * 128 + ((chunk ^ (rl & 7)) << 4));
+                    float y[4] = {q4.x, q4.y, q4.z, q4.w};
+                    float *dst = a.out + (mbase + rr) * a.N + nb;
+                    float rv[4] = {0.f, 0.f, 0.f, 0.f};
+                    if constexpr (RESID) {
+                        const uint4 rw = __ldg(reinterpret_cast<const uint4 *>(a.residual + (mbase + rr) * a.N + nb));
+                        if (a.residual_packed) { rv[0] = iss_unpack_split(rw.x); rv[1] = iss_unpack_split(rw.y); rv[2] = iss_unpack_split(rw.z); rv[3] = iss_unpack_split(rw.w); }
+                        else { rv[0] = __uint_as_float(rw.x); rv[1] = __uint_as_float(rw.y); rv[2] = __uint_as_float(rw.z); rv[3] = __uint_as_float(rw.w); }
+                    }
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        float t = y[q] + eb[q];
-                        if (pre) t = fmaf(t, es1[q], et1[q]);
-                        if (resid) t += rv[q];
+                        float t = fmaf(y[q], k1[q], k0[q]);
+                        if constexpr (RESID) t += rv[q];
                         if (relu) t = fmaxf(t, 0.f);
                         if (post) t = fmaf(t, es2[q], et2[q]);
                         y[q] = t;
                     }
-                    if (a.out_packed)
-                        *reinterpret_cast<uint4 *>(a.out + m * a.N + nb) = make_uint4(iss_pack_split(y[0]), iss_pack_split(y[1]), iss_pack_split(y[2]), iss_pack_split(y[3]));
+                    if constexpr (OUT_PACKED)
+                        *reinterpret_cast<uint4 *>(dst) = make_uint4(iss_pack_split(y[0]), iss_pack_split(y[1]), iss_pack_split(y[2]), iss_pack_split(y[3]));
                     else
-                        *reinterpret_cast<float4 *>(a.out + m * a.N + nb) = make_float4(y[0], y[1], y[2], y[3]);
+                        *reinterpret_cast<float4 *>(dst) = make_float4(y[0], y[1], y[2], y[3]);
                 }
-            }
+            };
+            if (resid) { if (a.out_packed) rows(std::true_type{}, std::true_type{}); else rows(std::false_type{}, std::true_type{}); }
+            else { if (a.out_packed) rows(std::true_type{}, std::false_type{}); else rows(std::false_type{}, std::false_type{}); }
+            __syncwarp();
         }
         tc_fence_before();
     } else {
@@ -457,7 +488,7 @@ int launch_tc3h(const ConvArgs &a, const F16Args &h, int slab_bytes, cudaStream_
 // k-block of MMAs (448 cycles) -- with two stages every k-block waited for its weights.
 // n-tile width: 128 output channels per CTA (one CTA per SM) when N allows it, else 64 (two CTAs per SM).
 // ISS_B200_F16_BN=64 forces 64 everywhere (experiment: the slab fill / epilogue of one CTA then overlaps the other's main loop).
-static int f16_bn_for(int N)
+int iss_f16_bn_for(int N)
 {
     static const int forced = [] { const char *e = getenv("ISS_B200_F16_BN"); return e ? atoi(e) : 0; }();
     if (forced == 64) return 64;
@@ -473,7 +504,7 @@ static int slab_plan(const ConvArgs &a, int *R_out, int *rows_out, int *tpi_out)
     const int tiles_img = (a.OH + R - 1) / R;
     const double eff_straddle = (double)(R * a.OW) / TBM, eff_img = (double)(a.OH * a.OW) / ((double)tiles_img * TBM);
     static const bool tpi_off = [] { const char *e = getenv("ISS_B200_F16_TPI"); return e && e[0] == '0'; }();   // A/B experiments
-    if (!tpi_off && f16_bn_for(a.N) == 64 && R <= a.OH && eff_img >= 0.92 * eff_straddle) { tpi = tiles_img; rows = R + a.KH - 1; }
+    if (!tpi_off && iss_f16_bn_for(a.N) == 64 && R <= a.OH && eff_img >= 0.92 * eff_straddle) { tpi = tiles_img; rows = R + a.KH - 1; }
     int slab_bytes = rows * a.W * a.C * 4;
     if (slab_bytes < 32768) slab_bytes = 32768;                  // doubles as the 4 x 4 KB epilogue transpose buffers
     *R_out = R; *rows_out = rows; *tpi_out = tpi;
@@ -489,7 +520,7 @@ bool iss_conv_f16_slab_covers(const ConvArgs &a)
     if (a.N % 64 != 0 || a.C % HBK != 0 || a.K % HBK != 0) return false;
     int R, rows, tpi;
     const int slab_bytes = slab_plan(a, &R, &rows, &tpi);
-    if (f16_bn_for(a.N) == 128) return TcHCfg<128, 2, 4>::FIXED + slab_bytes <= SMEM_CTA_MAX;
+    if (iss_f16_bn_for(a.N) == 128) return TcHCfg<128, 2, 4>::FIXED + slab_bytes <= SMEM_CTA_MAX;
     return TcHCfg<64, 3, 2>::FIXED + slab_bytes <= SMEM_CTA_MAX;
 }
 
@@ -503,7 +534,7 @@ int iss_launch_conv_tc_f16(ConvArgs &a, cudaStream_t st)
     a.slab_tpi = tpi;
     a.slab_rows = rows;
     a.in_elems = a.M / ((int64_t)a.OH * a.OW) * a.H * a.W * a.C;
-    const int BN = f16_bn_for(a.N);                              // same n-tiling as iss_prepare_f16_weights
+    const int BN = iss_f16_bn_for(a.N);                              // same n-tiling as iss_prepare_f16_weights
     F16Args h{reinterpret_cast<const unsigned char *>(a.wt_f16), a.wt_f16_inv_scale};
     if (BN == 128) {
         if (TcHCfg<128, 4, 4>::FIXED + slab_bytes <= SMEM_CTA_MAX) return launch_tc3h<128, 4, 4>(a, h, slab_bytes, st);
@@ -528,7 +559,7 @@ int iss_prepare_f16_weights(const float *h_w, int K, int N, void **d_out, float 
     for (int k = 0; k < K; ++k)
         for (int n = 0; n < N; ++n) wt[(size_t)n * K + k] = h_w[(size_t)k * N + n];
     std::vector<__half> img;
-    const float scale = iss_f16_build_image(wt.data(), N, K, K, f16_bn_for(N), img);
+    const float scale = iss_f16_build_image(wt.data(), N, K, K, iss_f16_bn_for(N), img);
     void *d = nullptr;
     cudaError_t e = cudaMalloc(&d, img.size() * sizeof(__half));
     if (e != cudaSuccess) { iss_set_error("cudaMalloc f16 weights: %s", cudaGetErrorString(e)); return ISS_ERR_NOMEM; }

@@ -26,6 +26,8 @@ struct RConv {
     int64_t w_off, scale_off, shift_off;
     float *d_wt = nullptr;      // tensor-core weights [2][N][Kp]
     int Kp = 0;
+    void *d_wt_f16 = nullptr;   // fp16 hi/lo image of engine 3 (cin % 64 == 0 && cout % 64 == 0: every conv of stages 2-4)
+    float f16_inv_scale = 1.f;
 };
 
 struct RBlock {
@@ -180,7 +182,9 @@ extern "C" int iss_resnet_create(iss_ctx *ctx, const float *h_blob, int64_t blob
     auto prep = [&](RConv &c) -> int {
         const int K = c.kh * c.kw * c.cin;
         if (c.cin % 32 != 0 || K % 32 != 0 || c.cout % 32 != 0) return ISS_OK;
-        return iss_prepare_tc_weights(h_blob + c.w_off, K, c.cout, &c.d_wt, &c.Kp);
+        const int rc = iss_prepare_tc_weights(h_blob + c.w_off, K, c.cout, &c.d_wt, &c.Kp);
+        if (rc != ISS_OK || c.cin % 64 != 0) return rc;
+        return iss_prepare_f16_weights(h_blob + c.w_off, K, c.cout, &c.d_wt_f16, &c.f16_inv_scale);
     };
     int prc = ISS_OK;
     for (RBlock &b : net->blocks) {
@@ -205,10 +209,11 @@ extern "C" int iss_resnet_destroy(iss_resnet *net)
     if (net->d_blob) cudaFree(net->d_blob);
     if (net->d_emb_wt) cudaFree(net->d_emb_wt);
     for (RBlock &b : net->blocks) {
-        if (b.c1.d_wt) cudaFree(b.c1.d_wt);
-        if (b.c2.d_wt) cudaFree(b.c2.d_wt);
-        if (b.c3.d_wt) cudaFree(b.c3.d_wt);
-        if (b.has_sc && b.sc.d_wt) cudaFree(b.sc.d_wt);
+        for (RConv *c : {&b.c1, &b.c2, &b.c3, &b.sc}) {
+            if (c == &b.sc && !b.has_sc) continue;
+            if (c->d_wt) cudaFree(c->d_wt);
+            if (c->d_wt_f16) cudaFree(c->d_wt_f16);
+        }
     }
     delete net;
     return ISS_OK;
@@ -264,12 +269,18 @@ extern "C" int iss_resnet_embed(iss_ctx *ctx, iss_resnet *net, const float *d_fe
     ISS_CUDA_OK(cudaMemcpyAsync(d_start, h_win_start, sizeof(int32_t) * n_windows, cudaMemcpyHostToDevice, st));
     const float *blob = net->d_blob;
 
-    auto conv = [&](const RConv &c, const float *in, float *out, int nb, int h, int w, int oh, int ow, int flags,
-                    const float *residual) -> int {
+    // Activation formats (conv_gemm.cuh): a tensor is stored as split-half words when its producer AND every consumer run on
+    // the fp16-split engine (all convolutions with cin % 64 == 0 and cout % 64 == 0, i.e. stages 2-4), fp32 otherwise.
+    const bool f16_mode = iss_get_gemm_mode() == ISS_GEMM_TC_F16;
+    auto f16 = [&](const RConv &c) { return f16_mode && c.d_wt_f16 != nullptr; };
+    auto conv = [&](const RConv &c, const float *in, bool in_packed, float *out, bool out_packed, int nb, int h, int w, int oh, int ow,
+                    int flags, const float *residual, bool residual_packed) -> int {
         ConvArgs a = {};
         a.in = in; a.w = blob + c.w_off; a.pre_scale = blob + c.scale_off; a.pre_shift = blob + c.shift_off;
         a.residual = residual; a.out = out;
         if (c.d_wt) { a.wt_hi = c.d_wt; a.wt_lo = c.d_wt + (size_t)c.cout * c.Kp; a.wt_tiled = c.d_wt + 2 * (size_t)c.cout * c.Kp; a.Kp = c.Kp; }
+        a.wt_f16 = c.d_wt_f16; a.wt_f16_inv_scale = c.f16_inv_scale;
+        a.in_packed = in_packed; a.out_packed = out_packed; a.residual_packed = residual_packed;
         a.M = (int64_t)nb * oh * ow; a.N = c.cout; a.K = c.kh * c.kw * c.cin;
         a.H = h; a.W = w; a.C = c.cin; a.OH = oh; a.OW = ow;
         a.KH = c.kh; a.KW = c.kw; a.SH = c.stride; a.SW = c.stride; a.PT = c.pad; a.PL = c.pad;
@@ -285,17 +296,32 @@ extern "C" int iss_resnet_embed(iss_ctx *ctx, iss_resnet *net, const float *d_fe
         iss_count_launch();
         int h = F, w = T;
         float *X = buf[0], *Y = buf[1], *A = buf[2], *Bf = buf[3], *S = buf[4];
-        int rc = conv(net->stem, in0, X, nb, h, w, h, w, ISS_F_RELU, nullptr);
+        int rc = conv(net->stem, in0, false, X, false, nb, h, w, h, w, ISS_F_RELU, nullptr, false);
         if (rc != ISS_OK) return rc;
-        for (const RBlock &b : net->blocks) {
+        bool x_packed = false;                                   // format of the block input X
+        for (size_t bi = 0; bi < net->blocks.size(); ++bi) {
+            const RBlock &b = net->blocks[bi];
             const int s = b.c2.stride;
             const int h2 = out_dim(h, 3, s, 1), w2 = out_dim(w, 3, s, 1);
-            rc = conv(b.c1, X, A, nb, h, w, h, w, ISS_F_RELU, nullptr);                 if (rc != ISS_OK) return rc;
-            rc = conv(b.c2, A, Bf, nb, h, w, h2, w2, ISS_F_RELU, nullptr);              if (rc != ISS_OK) return rc;
+            const bool a_packed = f16(b.c1) && f16(b.c2);        // c1 -> c2
+            const bool b_packed = f16(b.c2) && f16(b.c3);        // c2 -> c3
+            const bool s_packed = b.has_sc && f16(b.sc) && f16(b.c3);          // shortcut -> residual of c3
+            bool y_packed = false;                               // c3 -> next block (its c1, its shortcut conv, the residual of its c3)
+            if (bi + 1 < net->blocks.size()) {
+                const RBlock &nx = net->blocks[bi + 1];
+                y_packed = f16(b.c3) && f16(nx.c1) && f16(nx.c3) && (!nx.has_sc || f16(nx.sc));
+            }
+            rc = conv(b.c1, X, x_packed, A, a_packed, nb, h, w, h, w, ISS_F_RELU, nullptr, false);          if (rc != ISS_OK) return rc;
+            rc = conv(b.c2, A, a_packed, Bf, b_packed, nb, h, w, h2, w2, ISS_F_RELU, nullptr, false);       if (rc != ISS_OK) return rc;
             const float *res = X;
-            if (b.has_sc) { rc = conv(b.sc, X, S, nb, h, w, h2, w2, 0, nullptr);        if (rc != ISS_OK) return rc; res = S; }
-            rc = conv(b.c3, Bf, Y, nb, h2, w2, h2, w2, ISS_F_RELU, res);                if (rc != ISS_OK) return rc;
+            bool res_packed = x_packed;
+            if (b.has_sc) {
+                rc = conv(b.sc, X, x_packed, S, s_packed, nb, h, w, h2, w2, 0, nullptr, false);             if (rc != ISS_OK) return rc;
+                res = S; res_packed = s_packed;
+            }
+            rc = conv(b.c3, Bf, b_packed, Y, y_packed, nb, h2, w2, h2, w2, ISS_F_RELU, res, res_packed);    if (rc != ISS_OK) return rc;
             std::swap(X, Y);
+            x_packed = y_packed;
             h = h2; w = w2;
         }
         const int64_t np = (int64_t)nb * h * net->c_final;

@@ -25,6 +25,13 @@ def rep_summary(path):
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     out = ['# %s  (ncu --set full --clock-control none; per launch, cold cache, serialised)' % path]
+    try:                                   # stamp: bench.py only quotes `traffic` from a summary captured from the current kernel sources
+        import os
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from bench import kernel_source_hash
+        out.append('# source_sha256: ' + kernel_source_hash())
+    except Exception:
+        pass
     for r in rows[2:]:
         out.append('kernel: ' + r[hdr.index('Kernel Name')][:150])
         for k in KEYS:
