@@ -361,6 +361,7 @@ extern "C" int iss_get_gemm_mode(void)
 
 int iss_launch_conv_tc_f16(ConvArgs &a, cudaStream_t st);              // conv_gemm_tc_f16.cu; 1 = layer not covered
 int iss_launch_conv_tc_f16g(const ConvArgs &a, cudaStream_t st);       // conv_gemm_tc_f16g.cu; 1 = layer not covered
+int iss_launch_conv_tc_f16d(ConvArgs &a, cudaStream_t st);              // conv_gemm_tc_f16d.cu; 1 = layer not covered
 
 bool iss_conv_tc_eligible(const ConvArgs &a)
 {
@@ -370,8 +371,10 @@ bool iss_conv_tc_eligible(const ConvArgs &a)
 int iss_launch_conv_tc(const ConvArgs &a_in, int mode, cudaStream_t st)
 {
     ConvArgs a = a_in;
-    if (mode == ISS_GEMM_TC_F16) {                                      // fp16-split kernels where they apply: slab, then gather
-        int rc = iss_launch_conv_tc_f16(a, st);
+    if (mode == ISS_GEMM_TC_F16) {                                      // fp16-split kernels where they apply: direct, slab, then gather
+        int rc = iss_launch_conv_tc_f16d(a, st);
+        if (rc != 1) return rc;
+        rc = iss_launch_conv_tc_f16(a, st);
         if (rc != 1) return rc;
         static const bool gather_off = [] { const char *e = getenv("ISS_B200_F16_GATHER"); return e && e[0] == '0'; }();   // A/B experiments
         if (!gather_off || a.in_packed || a.out_packed || a.residual_packed) {

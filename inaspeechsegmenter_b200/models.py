@@ -89,6 +89,7 @@ def lower_keras_model(config, weights, in_h, in_w, allow_no_head=False):
     h, w, c = in_h, in_w, 1
     flat = False
     cur = None                 # the GEMM-like layer whose epilogue can still absorb ops
+    softmax_layers = []        # iss_cnn_forward honours softmax on the head only
 
     def apply_act(name):
         nonlocal cur
@@ -96,14 +97,21 @@ def lower_keras_model(config, weights, in_h, in_w, allow_no_head=False):
             return
         if cur is None:
             raise NotImplementedError('activation %r without a preceding Conv2D/Dense' % name)
+        # the kernels' epilogue order is fixed: bias -> affine(pre) -> ReLU -> sigmoid -> affine(post); anything a
+        # model asks for in another order is refused rather than silently reordered
         if name == 'relu':
-            if cur['flags'] & (_lib.F_RELU | _lib.F_AFFINE_POST | _lib.F_SOFTMAX):
+            if cur['flags'] & (_lib.F_RELU | _lib.F_SIGMOID | _lib.F_AFFINE_POST | _lib.F_SOFTMAX):
                 raise NotImplementedError('activation chain too long to fuse')
             cur['flags'] |= _lib.F_RELU
         elif name == 'softmax':
+            if cur['flags'] & (_lib.F_RELU | _lib.F_SIGMOID | _lib.F_AFFINE_POST | _lib.F_SOFTMAX):
+                raise NotImplementedError('softmax after another activation')
             cur['flags'] |= _lib.F_SOFTMAX
+            softmax_layers.append(cur)
             cur = None
         elif name == 'sigmoid':
+            if cur['flags'] & (_lib.F_SIGMOID | _lib.F_AFFINE_POST | _lib.F_SOFTMAX):
+                raise NotImplementedError('sigmoid after an activation the epilogue evaluates later')
             cur['flags'] |= _lib.F_SIGMOID
         else:
             raise NotImplementedError('activation %r' % name)
@@ -196,6 +204,8 @@ def lower_keras_model(config, weights, in_h, in_w, allow_no_head=False):
             cur = None
         else:
             raise NotImplementedError('Keras layer %s is not supported by the B200 CNN operator' % cls)
+    if any(d is not descs[-1] for d in softmax_layers):
+        raise NotImplementedError('softmax on a layer that is not the head')
     if not (h == 1 and w == 1) and not (allow_no_head and flat):
         raise NotImplementedError('model must end in a Dense head')
     return LoweredModel(descs, np.concatenate(blob) if blob else np.zeros(0, np.float32), in_h, in_w, c,

@@ -11,6 +11,7 @@ Host code only moves bytes (pinned host -> device, small label arrays back),
 run-length-encodes label tracks (_binidx2seglist, :91-108) and formats output.
 """
 import os
+import zlib
 import random
 import shutil
 import sys
@@ -114,7 +115,7 @@ class DnnSegmenter:
             if path is None:
                 if os.environ.get('ISS_B200_SYNTHETIC_MODELS') == '1':
                     warnings.warn('%s not found: using a SYNTHETIC stand-in network (labels are meaningless)' % self.model_fname)
-                    model = models.synthetic_keras_cnn(self.nmel, len(self.outlabels), seed=hash(self.model_fname) % 1000)
+                    model = models.synthetic_keras_cnn(self.nmel, len(self.outlabels), seed=zlib.crc32(self.model_fname.encode()) % 1000)
                 else:
                     raise FileNotFoundError(
                         '%s not found in $%s, /root/.keras/inaSpeechSegmenter or ~/.keras/inaSpeechSegmenter '

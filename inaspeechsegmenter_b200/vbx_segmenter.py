@@ -155,29 +155,20 @@ class VBxExtractor(ABC):
         pass
 
     def __call__(self, basename, fea, duration):
-        xvectors = []
-        start = 0
-        for start in range(0, len(fea) - WINLEN, STEP):
-            data = fea[start:start + WINLEN]
-            xvector = self.get_embedding(data)
-            key = f'{basename}_{start:08}-{(start + WINLEN):08}'
-            if np.isnan(xvector).any():
-                logger.warning(f'NaN found, not processing: {key}{os.linesep}')
-            else:
-                seg_start = round(start / 100.0, 3)
-                seg_end = round(start / 100.0 + WINLEN / 100.0, 3)
-                xvectors.append((key, (seg_start, seg_end), xvector))
-        if len(fea) - start - STEP >= 10:
-            data = fea[start + STEP:len(fea)]
-            xvector = self.get_embedding(data)
-            key = f'{basename}_{(start + STEP):08}-{len(fea):08}'
-            if np.isnan(xvector).any():
-                logger.warning(f'NaN found, not processing: {key}{os.linesep}')
-            else:
-                seg_start = round((start + STEP) / 100.0, 3)
-                seg_end = round(duration, 3)
-                xvectors.append((key, (seg_start, seg_end), xvector))
-        return [(key, seg, x * 10) for key, seg, x in xvectors]
+        """One get_embedding() call per planned window (vbx_segmenter.py:217-246): NaN embeddings are dropped with a
+        warning, the tail window ends at `duration`, embeddings are returned x10."""
+        out = []
+        for start, length, is_tail in window_plan(len(fea)):
+            stop = start + length
+            key = '%s_%08d-%08d' % (basename, start, stop)
+            x = self.get_embedding(fea[start:stop])
+            if np.isnan(x).any():
+                logger.warning('NaN found, not processing: %s%s' % (key, os.linesep))
+                continue
+            t0 = round(start / 100.0, 3)
+            t1 = round(duration, 3) if is_tail else round(start / 100.0 + WINLEN / 100.0, 3)
+            out.append((key, (t0, t1), x * 10))
+        return out
 
 
 def window_plan(M):

@@ -1,19 +1,21 @@
 #!/bin/bash
-# One GPU call: micro-tests, tests, A/B timings of whole-network variants, bench, launch list, ncu capture of the dominant kernel.
+# One GPU call: micro-tests, A/B timings of whole-network variants, tests, bench, launch list, ncu capture of the dominant kernel.
 # Usage: bash tools/gpu_round.sh <tag> [full|fast] [kernel-regex]
 set -u
-TAG=${1:-run}; MODE=${2:-fast}; KRE=${3:-conv_gemm_tc3h_kernel}
+TAG=${1:-run}; MODE=${2:-fast}; KRE=${3:-conv_gemm_tc4h_kernel}
 mkdir -p gpurun_out
 ( cd tools && nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o ../gpurun_out/umma_desc_offset_test umma_desc_offset_test.cu && timeout 120 ../gpurun_out/umma_desc_offset_test ) > gpurun_out/${TAG}_desc_test.log 2>&1
-( timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -40 ) > gpurun_out/${TAG}_pytest.log
 {
   timeout 200 python tools/tc_check.py 0 10 | grep -E "^mode"
-  echo "== default"; timeout 200 python tools/tc_check.py 3 10 | grep -E "^mode|rror"
-  echo "== ISS_B200_FUSE_FIRST=0"; ISS_B200_FUSE_FIRST=0 timeout 200 python tools/tc_check.py 3 10 | grep -E "^mode|rror"
-  echo "== ISS_B200_F16_GATHER=0"; ISS_B200_F16_GATHER=0 timeout 200 python tools/tc_check.py 3 10 | grep -E "^mode|rror"
+  echo "== ISS_B200_F16_DIRECT=0 (TMEM-operand slab kernel)"; ISS_B200_F16_DIRECT=0 timeout 200 python tools/tc_check.py 3 10 2>&1 | grep -E "^mode|rror|timed out"
+  echo "== default (direct kernel)"; timeout 200 python tools/tc_check.py 3 10 2>&1 | grep -E "^mode|rror|timed out"
+  echo "== ISS_B200_DESC_BASE_OFFSET=1"; ISS_B200_DESC_BASE_OFFSET=1 timeout 200 python tools/tc_check.py 3 10 2>&1 | grep -E "^mode|rror|timed out"
+  echo "== ISS_B200_FUSE_FIRST=0"; ISS_B200_FUSE_FIRST=0 timeout 200 python tools/tc_check.py 3 10 2>&1 | grep -E "^mode|rror|timed out"
   echo "== resnet"; timeout 300 python tests/tools/resnet_check.py 2>&1 | grep -E "^mode|rror|Trace"
   echo "== resnet ISS_B200_F16_GATHER=0"; ISS_B200_F16_GATHER=0 timeout 300 python tests/tools/resnet_check.py 2>&1 | grep -E "^mode 3|rror|Trace"
 } > gpurun_out/${TAG}_ab.log 2>&1
+( timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -40 ) > gpurun_out/${TAG}_pytest.log
+( ISS_B200_F16_DIRECT=0 timeout 600 python bench.py --no-extras --no-cpu-baseline 2>gpurun_out/${TAG}_bench_base.err ) > gpurun_out/${TAG}_bench_base.json
 if [ "$MODE" = full ]; then
   ( timeout 900 python bench.py 2>gpurun_out/${TAG}_bench.err ) > gpurun_out/${TAG}_bench.json
 else
@@ -23,4 +25,4 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --lo
     python bench.py --hours 0.5 --steps 1 --warmup 1 --no-cpu-baseline --no-extras > gpurun_out/${TAG}_ncu_launch.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:${KRE} -s 6 -c 2 -f -o gpurun_out/${TAG}_prof \
     python bench.py --hours 0.5 --steps 1 --warmup 1 --no-cpu-baseline --no-extras > gpurun_out/${TAG}_ncu_full.log 2>&1
-cat gpurun_out/${TAG}_desc_test.log; tail -12 gpurun_out/${TAG}_pytest.log; cat gpurun_out/${TAG}_ab.log; head -c 2500 gpurun_out/${TAG}_bench.json; tail -c 600 gpurun_out/${TAG}_bench.err
+cat gpurun_out/${TAG}_desc_test.log; cat gpurun_out/${TAG}_ab.log; tail -12 gpurun_out/${TAG}_pytest.log; head -c 1500 gpurun_out/${TAG}_bench_base.json; echo; head -c 2500 gpurun_out/${TAG}_bench.json; tail -c 600 gpurun_out/${TAG}_bench.err
