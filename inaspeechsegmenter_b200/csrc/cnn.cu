@@ -206,12 +206,13 @@ conv_first_direct_kernel(const FirstArgs a)
 
 // ------------------------------------------------------------------ first layer by linearity (FirstFuse, conv_gemm.cuh)
 // Y[r][x][c] = sum_{kh,kw} w[kh][kw][c] * mspec[f0 + r + kh][x + kw] in float64, for the frames a batch of patches
-// covers; one thread = one (row, column) position and 4 channels, filter in shared memory.
+// covers, stored as the two-float number Yh + Yl (FirstFuse, conv_gemm.cuh); one thread = one (row, column) position
+// and 4 channels, filter in shared memory.
 __global__ void __launch_bounds__(256)
 first_linear_kernel(const float *__restrict__ mspec, int ld, int64_t f0, int64_t rows, int64_t n_frames, int OW, int KH, int KW, int C,
-                    const float *__restrict__ w, double *__restrict__ Y)
+                    const float *__restrict__ w, float *__restrict__ Yh, float *__restrict__ Yl)
 {
-    extern __shared__ __align__(16) float wsm[];               // [KH * KW][C]
+    extern __shared__ __align__(16) float wsm[];               // [KH * KW][C]  (float64 weights in shared memory measured slower: 61 vs 47 us)
     for (int i = threadIdx.x; i < KH * KW * C; i += 256) wsm[i] = w[i];
     __syncthreads();
     const int CQ = C >> 2;
@@ -233,9 +234,32 @@ first_linear_kernel(const float *__restrict__ mspec, int ld, int64_t f0, int64_t
             acc[2] = fma(xv, (double)w4.z, acc[2]); acc[3] = fma(xv, (double)w4.w, acc[3]);
         }
     }
-    double2 *dst = reinterpret_cast<double2 *>(Y + (r * OW + x) * (int64_t)C + c4 * 4);
-    dst[0] = make_double2(acc[0], acc[1]);
-    dst[1] = make_double2(acc[2], acc[3]);
+    float h[4], l[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { h[q] = (float)acc[q]; l[q] = (float)(acc[q] - (double)h[q]); }
+    const int64_t o = (r * OW + x) * (int64_t)C + c4 * 4;
+    *reinterpret_cast<float4 *>(Yh + o) = make_float4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<float4 *>(Yl + o) = make_float4(l[0], l[1], l[2], l[3]);
+}
+
+// Per (patch, channel) coefficients of the fused first layer (FirstFuse): alpha = s_c / sigma_j rounded to float32,
+// beta = (b_c s_c + t_c) - mu_j S_c alpha in float64 (from the ROUNDED alpha), stored as two floats.  coef[j][3][C].
+__global__ void __launch_bounds__(256)
+first_coef_kernel(const float *__restrict__ mu, const float *__restrict__ sigma, const double *__restrict__ S,
+                  const float *__restrict__ bias, const float *__restrict__ pre_scale, const float *__restrict__ pre_shift,
+                  int64_t n, int C, float *__restrict__ coef)
+{
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n * C) return;
+    const int c = (int)(i % C);
+    const int64_t j = i / C;
+    const double s1 = pre_scale ? (double)pre_scale[c] : 1.0, t1 = pre_shift ? (double)pre_shift[c] : 0.0;
+    const double b = bias ? (double)bias[c] : 0.0;
+    const float alpha = (float)(s1 / (double)sigma[j]);
+    const double beta = (b * s1 + t1) - (double)mu[j] * S[c] * (double)alpha;
+    const float bh = (float)beta;
+    float *dst = coef + j * 3 * C + c;
+    dst[0] = alpha; dst[C] = bh; dst[2 * C] = (float)(beta - (double)bh);
 }
 
 // ------------------------------------------------------------------ max pooling (NHWC)
@@ -464,14 +488,15 @@ extern "C" int iss_cnn_num_classes(const iss_cnn *cnn) { return cnn ? cnn->n_cla
 extern "C" double iss_cnn_flops_per_patch(const iss_cnn *cnn) { return cnn ? cnn->flops : 0.0; }
 
 namespace {
-// rows of the float64 first-layer map a batch of B patches may need (3x the contiguous case; batches whose
+// rows of the two-float first-layer map a batch of B patches may need (3x the contiguous case; batches whose
 // patches are spread wider fall back to the un-fused first layer) and its size in bytes (0: no fusion possible)
 int64_t first_y_rows(int64_t B) { return 3 * (PATCH_HOP * B + PATCH_H); }
 size_t first_y_bytes(const iss_cnn *cnn, int64_t B)
 {
     if (!cnn->d_first_S || cnn->layers.size() < 2) return 0;
     const Layer &L0 = cnn->layers[0];
-    return align_up((size_t)first_y_rows(B) * L0.out_w * L0.out_c * sizeof(double), 256);
+    return 2 * align_up((size_t)first_y_rows(B) * L0.out_w * L0.out_c * sizeof(float), 256) +        // Yh, Yl
+           align_up((size_t)B * 3 * L0.out_c * sizeof(float), 256);                                   // per-patch coefficients
 }
 }  // namespace
 
@@ -580,7 +605,14 @@ extern "C" int iss_cnn_forward(iss_ctx *ctx, iss_cnn *cnn, const float *d_mspec,
     act[1] = reinterpret_cast<float *>(p + o);    o += align_up((size_t)B * cnn->max_act * 4, 256);
     int32_t *d_seg_start = reinterpret_cast<int32_t *>(p + o); o += align_up((size_t)(n_seg + 1) * 4, 256);
     int64_t *d_seg_off = reinterpret_cast<int64_t *>(p + o);   o += align_up((size_t)(n_seg + 1) * 8, 256);
-    double *d_first_y = first_y_bytes(cnn, B) ? reinterpret_cast<double *>(p + o) : nullptr;  o += first_y_bytes(cnn, B);
+    float *d_first_yh = nullptr, *d_first_yl = nullptr, *d_first_coef = nullptr;                // fused first layer (FirstFuse)
+    if (first_y_bytes(cnn, B)) {
+        const Layer &L0 = cnn->layers[0];
+        const size_t plane = align_up((size_t)first_y_rows(B) * L0.out_w * L0.out_c * sizeof(float), 256);
+        d_first_yh = reinterpret_cast<float *>(p + o); d_first_yl = reinterpret_cast<float *>(p + o + plane);
+        d_first_coef = reinterpret_cast<float *>(p + o + 2 * plane);
+        o += first_y_bytes(cnn, B);
+    }
     // host copy of patch_index_kernel's arithmetic: first log-mel frame of patch i (for the span of a batch)
     auto host_row0 = [&](int64_t i) -> int64_t {
         int lo = 0, hi = n_seg;
@@ -609,6 +641,7 @@ extern "C" int iss_cnn_forward(iss_ctx *ctx, iss_cnn *cnn, const float *d_mspec,
         bool cur_packed = false;                                 // format of `cur`: fp32 values or split-half words
         FirstFuse ffuse = {};                                    // set by layer 0 when it is folded into layer 1's slab fill
         bool first_fused = false;
+        int pend_pool_h = 0, pend_pool_w = 0;                    // un-pooled dims of a MaxPooling2D folded into the next convolution
         for (size_t li = 0; li < cnn->layers.size(); ++li) {
             const Layer &Lr = cnn->layers[li];
             const iss_layer_desc &d = Lr.d;
@@ -624,6 +657,22 @@ extern "C" int iss_cnn_forward(iss_ctx *ctx, iss_cnn *cnn, const float *d_mspec,
                     }
                 }
                 ISS_CUDA_OK(cudaEventRecord(cnn->prof_ev[cnn->prof_used], st));
+            }
+            if (d.kind == ISS_LAYER_MAXPOOL && cur_packed && li > 0 && li + 1 < cnn->layers.size()) {
+                // 2x2 / stride-2 'valid' pooling in front of a convolution the direct kernel takes: the maximum is taken in that
+                // kernel's slab fill (conv_gemm_tc_f16d.cu, IN_POOL) and this layer never runs.  ISS_B200_FUSE_POOL=0: A/B tests.
+                static const bool pool_off = [] { const char *e = getenv("ISS_B200_FUSE_POOL"); return e && e[0] == '0'; }();
+                const Layer &Nx = cnn->layers[li + 1];
+                if (!pool_off && !prof && d.kh == 2 && d.kw == 2 && d.sh == 2 && d.sw == 2 && d.pad_top == 0 && d.pad_left == 0 &&
+                    d.pad_bottom == 0 && d.pad_right == 0 && Nx.d.kind == ISS_LAYER_CONV2D && Nx.d.pad_bottom == 0 && Nx.d.pad_right == 0 &&
+                    iss_get_gemm_mode() == ISS_GEMM_TC_F16) {
+                    ConvArgs pn = {};
+                    fill_conv_args(Nx, nb, pn);
+                    pn.in_packed = 1;
+                    pn.flags = Nx.d.flags & ~ISS_F_SOFTMAX;
+                    pn.pool_h = Lr.in_h; pn.pool_w = Lr.in_w;
+                    if (iss_conv_f16_direct_covers(pn)) { pend_pool_h = Lr.in_h; pend_pool_w = Lr.in_w; continue; }
+                }
             }
             if (d.kind == ISS_LAYER_MAXPOOL) {
                 ISS_REQUIRE(li > 0, ISS_ERR_UNSUPPORTED, "iss_cnn_forward: pooling as first layer is not supported");
@@ -666,26 +715,29 @@ extern "C" int iss_cnn_forward(iss_ctx *ctx, iss_cnn *cnn, const float *d_mspec,
                 // whose patches span few enough frames for the float64 map.
                 const char *fuse_env = getenv("ISS_B200_FUSE_FIRST");      // "0" = keep the stand-alone first-layer kernel (A/B tests)
                 const bool fuse_off = fuse_env && fuse_env[0] == '0';
-                bool next_is_slab = false;                       // the FIRST mode lives in the slab kernel only
+                bool next_is_direct = false;                     // the FIRST mode lives in the direct kernel only
                 if (li == 0 && cnn->layers.size() > 1 && cnn->layers[1].d.kind == ISS_LAYER_CONV2D &&
-                    cnn->layers[1].d.pad_bottom == 0 && cnn->layers[1].d.pad_right == 0) {
+                    cnn->layers[1].d.pad_bottom == 0 && cnn->layers[1].d.pad_right == 0 && iss_get_gemm_mode() == ISS_GEMM_TC_F16) {
                     ConvArgs p1 = {};
                     fill_conv_args(cnn->layers[1], nb, p1);
-                    next_is_slab = iss_conv_f16_slab_covers(p1);
+                    p1.in_packed = 1;
+                    p1.flags = cnn->layers[1].d.flags & ~ISS_F_SOFTMAX;
+                    next_is_direct = iss_conv_f16_direct_covers(p1);
                 }
-                if (li == 0 && direct && a.out_packed && !fuse_off && d_first_y && ranges_ascending && next_is_slab && 128 % (d.cout / 4) == 0 && d.sh == 1 && d.sw == 1 && d.pad_top == 0 && d.pad_left == 0 &&
-                    d.pad_bottom == 0 && d.pad_right == 0 && !(d.flags & ISS_F_SOFTMAX)) {
+                if (li == 0 && direct && a.out_packed && !fuse_off && d_first_yh && ranges_ascending && next_is_direct && d.sh == 1 && d.sw == 1 && d.pad_top == 0 && d.pad_left == 0 &&
+                    d.pad_bottom == 0 && d.pad_right == 0 && !(d.flags & (ISS_F_SOFTMAX | ISS_F_SIGMOID))) {
                     const int64_t f_first = host_row0(b0), f_last = host_row0(b0 + nb - 1);
                     const int64_t rows = f_last - f_first + Lr.out_h;
                     if (rows <= first_y_rows(B)) {
                         const int64_t work = rows * Lr.out_w * (d.cout >> 2);
                         first_linear_kernel<<<(unsigned)((work + 255) / 256), 256, (size_t)d.kh * d.kw * d.cout * sizeof(float), st>>>(
-                            d_mspec, ld, f_first, rows, L, Lr.out_w, d.kh, d.kw, d.cout, a.w, d_first_y);
+                            d_mspec, ld, f_first, rows, L, Lr.out_w, d.kh, d.kw, d.cout, a.w, d_first_yh, d_first_yl);
+                        first_coef_kernel<<<(unsigned)((nb * d.cout + 255) / 256), 256, 0, st>>>(
+                            pa.mu + b0, pa.sigma + b0, cnn->d_first_S, a.bias, a.pre_scale, a.pre_shift, nb, d.cout, d_first_coef);
                         ISS_CUDA_OK(cudaGetLastError());
-                        iss_count_launch();
-                        ffuse.Y = d_first_y; ffuse.y_f0 = f_first; ffuse.y_rows = rows;
-                        ffuse.row0 = pa.row0 + b0; ffuse.mu = pa.mu + b0; ffuse.sigma = pa.sigma + b0; ffuse.S = cnn->d_first_S;
-                        ffuse.bias = a.bias; ffuse.pre_scale = a.pre_scale; ffuse.pre_shift = a.pre_shift;
+                        iss_count_launch(2);
+                        ffuse.Yh = d_first_yh; ffuse.Yl = d_first_yl; ffuse.y_f0 = f_first; ffuse.y_rows = rows;
+                        ffuse.row0 = pa.row0 + b0; ffuse.coef = d_first_coef;
                         ffuse.post_scale = a.post_scale; ffuse.post_shift = a.post_shift; ffuse.flags = a.flags; ffuse.n_img = nb;
                         first_fused = true;
                     }
@@ -718,6 +770,8 @@ extern "C" int iss_cnn_forward(iss_ctx *ctx, iss_cnn *cnn, const float *d_mspec,
                     }
                 } else {
                     a.in = cur;
+                    a.pool_h = pend_pool_h; a.pool_w = pend_pool_w;
+                    pend_pool_h = pend_pool_w = 0;
                     if (li == 1 && first_fused) { a.first = &ffuse; a.in = nullptr; a.in_packed = 1; }
                     rc = iss_launch_conv(a, false, st);
                 }

@@ -173,6 +173,60 @@ conv_gemm_f32_kernel(const ConvArgs a)
 }
 
 
+// Dense / 1x1 layer with a handful of outputs (the softmax heads: 512 -> 2 or 3).  The generic 128 x 64 tile kernel spends
+// 48 us on this 6 MFLOP layer (one column of CTAs, 3 useful columns of 64); here one warp owns a GEMM row, the K dimension
+// is split over the lanes with 16-byte loads, the weights sit transposed [N][K] in shared memory (conflict-free float4
+// reads) and the lane partials are combined in a fixed order (xor tree): deterministic, independent of the grid.
+constexpr int SMALL_N = 8;
+__global__ void __launch_bounds__(256)
+dense_small_n_kernel(const ConvArgs a)
+{
+    extern __shared__ __align__(16) float wsm_t[];                 // [N][K]
+    for (int i = threadIdx.x; i < a.K * a.N; i += 256) { const int k = i / a.N, n = i - k * a.N; wsm_t[n * a.K + k] = a.w[i]; }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int K4 = a.K >> 2;
+    for (int64_t m = (int64_t)blockIdx.x * 8 + warp; m < a.M; m += (int64_t)gridDim.x * 8) {
+        const float4 *x = reinterpret_cast<const float4 *>(a.in + m * a.K);
+        float acc[SMALL_N];
+#pragma unroll
+        for (int n = 0; n < SMALL_N; ++n) acc[n] = 0.f;
+        for (int k4 = lane; k4 < K4; k4 += 32) {
+            const float4 v = __ldg(x + k4);
+#pragma unroll
+            for (int n = 0; n < SMALL_N; ++n) {
+                if (n < a.N) {
+                    const float4 w = *reinterpret_cast<const float4 *>(wsm_t + n * a.K + 4 * k4);
+                    acc[n] = fmaf(v.x, w.x, acc[n]); acc[n] = fmaf(v.y, w.y, acc[n]);
+                    acc[n] = fmaf(v.z, w.z, acc[n]); acc[n] = fmaf(v.w, w.w, acc[n]);
+                }
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < SMALL_N; ++n)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
+        if (lane < a.N) {
+            float xv = 0.f;
+#pragma unroll
+            for (int n = 0; n < SMALL_N; ++n) if (n == lane) xv = acc[n];
+            const int n = lane;
+            if (a.flags & ISS_F_BIAS) xv += a.bias[n];
+            if (a.flags & ISS_F_AFFINE_PRE) xv = fmaf(xv, a.pre_scale[n], a.pre_shift[n]);
+            if (a.flags & ISS_F_RELU) xv = fmaxf(xv, 0.f);
+            if (a.flags & ISS_F_SIGMOID) xv = 1.f / (1.f + expf(-xv));
+            if (a.flags & ISS_F_AFFINE_POST) xv = fmaf(xv, a.post_scale[n], a.post_shift[n]);
+            a.out[m * a.N + n] = xv;
+        }
+    }
+}
+
+bool small_n_covers(const ConvArgs &a)
+{
+    return a.KH == 1 && a.KW == 1 && a.SH == 1 && a.SW == 1 && a.PT == 0 && a.PL == 0 && a.N <= SMALL_N && a.K % 4 == 0 && a.K == a.C &&
+           (size_t)a.K * a.N * sizeof(float) <= 48 * 1024 && !a.in_packed && !a.out_packed && !(a.flags & ISS_F_RESIDUAL);
+}
+
 template <bool FIRST>
 int launch_conv_t(const ConvArgs &a, cudaStream_t st)
 {
@@ -194,6 +248,13 @@ int launch_conv_t(const ConvArgs &a, cudaStream_t st)
 
 int iss_launch_conv(const ConvArgs &a, bool first, cudaStream_t st)
 {
+    if (!first && small_n_covers(a)) {
+        const int64_t gm = (a.M + 7) / 8;
+        dense_small_n_kernel<<<(unsigned)(gm < 148 * 8 ? gm : 148 * 8), 256, (size_t)a.K * a.N * sizeof(float), st>>>(a);
+        ISS_CUDA_OK(cudaGetLastError());
+        iss_count_launch();
+        return ISS_OK;
+    }
     if (!first) {
         const int mode = iss_get_gemm_mode();
         if (mode != ISS_GEMM_FP32 && iss_conv_tc_eligible(a)) return iss_launch_conv_tc(a, mode, st);

@@ -12,6 +12,16 @@ __device__ __forceinline__ uint32_t iss_pack_split(float y)
     const __half ll = __float2half_rn(y - __half2float(hh));
     return (uint32_t)__half_as_ushort(hh) | ((uint32_t)__half_as_ushort(ll) << 16);
 }
+// two values at once: the pair conversions map to F2FP (full-rate ALU) instead of the scalar F2F (conversion unit)
+__device__ __forceinline__ void iss_pack_split2(float y0, float y1, uint32_t &w0, uint32_t &w1)
+{
+    const __half2 hh = __floats2half2_rn(y0, y1);
+    const float2 hf = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(y0 - hf.x, y1 - hf.y);
+    const uint32_t h = *reinterpret_cast<const uint32_t *>(&hh), l = *reinterpret_cast<const uint32_t *>(&ll);
+    w0 = __byte_perm(h, l, 0x5410);
+    w1 = __byte_perm(h, l, 0x7632);
+}
 __device__ __forceinline__ float iss_unpack_split(uint32_t w)
 {
     return __half2float(__ushort_as_half((unsigned short)(w & 0xFFFFu))) + __half2float(__ushort_as_half((unsigned short)(w >> 16)));
@@ -19,22 +29,26 @@ __device__ __forceinline__ float iss_unpack_split(uint32_t w)
 
 #define ISS_F_RESIDUAL 64     /* internal: + residual[m][n] after the pre-affine, before ReLU */
 
-// First layer folded into the slab fill of the convolution behind it (conv_gemm_tc_f16.cu, FIRST mode): the
+// First layer folded into the slab fill of the convolution behind it (conv_gemm_tc_f16d.cu, FIRST mode): the
 // first Conv2D of the segmenter CNNs has ONE input channel and its input is the z-normalised patch
 // (x - mu_j) / sigma_j (segmenter.py:82), so by linearity
 //     conv(x^)[t, f, c] = (Y[row0_j + t, f, c] - mu_j * S_c) / sigma_j,   Y = conv(raw log-mel), S_c = sum of the filter
-// and Y is shared by all the patches that overlap a frame (97 % overlap: hop 2 of 68 frames).  Y is computed once
-// per batch in float64 (first_linear_kernel); the slab fill of the next convolution evaluates the expression
-// above + the first layer's bias / BatchNorm / ReLU epilogue and writes split-half words straight into shared
-// memory: the first layer's output (283 KB per patch, 47 % of all activation traffic) never exists in HBM.
+// and Y is shared by all the patches that overlap a frame (97 % overlap: hop 2 of 68 frames).  Y is computed once per
+// batch in float64 and stored as a two-float number Yh + Yl (first_linear_kernel); bias and the BatchNorm affine
+// (scale s_c, shift t_c) fold with the normalisation into ONE multiply-add per value,
+//     a[t, f, c] = Y * alpha_jc + beta_jc,   alpha_jc = s_c / sigma_j,   beta_jc = (b_c s_c + t_c) - mu_j S_c alpha_jc,
+// with alpha rounded to float32 FIRST and beta (float64, stored as two floats) computed from the rounded alpha, so the
+// cancellation between Y alpha and beta is exact to ~1e-7 relative (first_coef_kernel).  The slab fill evaluates
+// fma(Yh, alpha, beta_h) + fma(Yl, alpha, beta_l), ReLU, the optional second affine, and writes fp16 hi / lo planes
+// straight into shared memory: the first layer's output (283 KB per patch, 47 % of all activation traffic) never
+// exists in HBM.
 struct FirstFuse {
-    const double *Y;                // [y_rows][W * C] float64, row r = conv of log-mel frames y_f0 + r ..
+    const float *Yh, *Yl;           // [y_rows][W * C] each, row r = conv of log-mel frames y_f0 + r ..; Y = Yh + Yl
     int64_t y_f0;                   // log-mel frame of Y row 0
     int64_t y_rows;
     const int32_t *row0;            // per patch of the batch: first log-mel frame
-    const float *mu, *sigma;        // per patch: statistics of the patch (float32, as the reference computes them)
-    const double *S;                // [C] sum of the first layer's filter taps, float64
-    const float *bias, *pre_scale, *pre_shift, *post_scale, *post_shift;   // first layer's epilogue (nullptr = absent)
+    const float *coef;              // per patch [3][C]: alpha, beta_hi, beta_lo
+    const float *post_scale, *post_shift;   // first layer's affine behind the ReLU (nullptr = absent)
     int flags;                      // ISS_F_* of the first layer
     int64_t n_img;                  // patches in the batch
 };
@@ -61,7 +75,8 @@ struct ConvArgs {
     // activation formats of that engine: fp32 values (0) or split-half words lo16 << 16 | hi16 (1)
     int in_packed, out_packed;
     int residual_packed;    // `residual` holds split-half words (fp16-split kernels only)
-    const FirstFuse *first;         // host pointer, non-null: FIRST mode (copied into the kernel parameters)
+    int pool_h, pool_w;     // direct kernel only, > 0: `in` is the un-pooled [n][pool_h][pool_w][C] tensor, 2x2 / stride-2 max taken in the slab fill
+    const FirstFuse *first;         // host pointer, non-null: FIRST mode of the direct kernel (copied into the kernel parameters)
     // slab kernel (conv_gemm_tc_f16.cu) only, filled in by iss_launch_conv_tc_f16
     int slab_R;             // output rows (of width OW) per 128-row GEMM tile
     int slab_rows;          // input rows the slab is sized for
@@ -85,6 +100,9 @@ int iss_prepare_tc_weights(const float *h_w, int K, int N, float **d_out, int *K
 int iss_prepare_f16_weights(const float *h_w, int K, int N, void **d_out, float *inv_scale);
 // does engine 3's slab kernel cover this layer (geometry + prepared image + shared memory)?
 bool iss_conv_f16_slab_covers(const ConvArgs &a);
+// does engine 3's direct kernel (conv_gemm_tc_f16d.cu: both operands from shared memory) cover this layer?  It reads
+// split-half words (a.in_packed) or, with a.first set, evaluates the one-channel first layer in its slab fill
+bool iss_conv_f16_direct_covers(const ConvArgs &a);
 // does engine 3's gather kernel (conv_gemm_tc_f16g.cu: any stride / padding / 1x1) cover this layer?
 bool iss_conv_f16_gather_covers(const ConvArgs &a);
 // n-tile width of engine 3 for N output channels (must agree between the weight image and the launch)

@@ -84,15 +84,14 @@ __device__ __forceinline__ uint4 lds128u(uint32_t addr)
     return v;
 }
 
-// MODE: how the input slab is obtained -- IN_F32: fp32 activations, split in the A producers; IN_PACKED: split-half
-// words (see the file header); IN_FIRST: the layer in front is the one-channel first convolution of a segmenter CNN
-// and is evaluated INSIDE the slab fill from the shared float64 map Y (FirstFuse, conv_gemm.cuh) -- the slab then
-// holds split-half words like IN_PACKED.  a.out_packed selects the output format.
-constexpr int IN_F32 = 0, IN_PACKED = 1, IN_FIRST = 2;
+// MODE: format of the input tensor -- IN_F32: fp32 activations, split in the A producers; IN_PACKED: split-half
+// words (see the file header).  a.out_packed selects the output format.  (The fused first layer lives in the
+// direct kernel, conv_gemm_tc_f16d.cu.)
+constexpr int IN_F32 = 0, IN_PACKED = 1;
 
 template <int BN, int SB, int ST, int MODE>
 __global__ void __launch_bounds__(160, (TcHCfg<BN, SB, ST>::TMEM_COLS <= 256 ? 2 : 1))
-conv_gemm_tc3h_kernel(const ConvArgs a, const F16Args h, const FirstFuse ff)
+conv_gemm_tc3h_kernel(const ConvArgs a, const F16Args h)
 {
     constexpr bool PACKED = MODE != IN_F32;
     using Cfg = TcHCfg<BN, SB, ST>;
@@ -159,91 +158,7 @@ conv_gemm_tc3h_kernel(const ConvArgs a, const F16Args h, const FirstFuse ff)
             const int total = rows * a.W * cpp;
             int p = tid / cpp, j = tid - p * cpp;
             const int dp = 128 / cpp, dj = 128 - dp * cpp;
-            if constexpr (MODE == IN_FIRST) {
-                // 128 % cpp == 0 (checked by the launcher): a thread keeps its 4 channels (chunk jc) for the whole fill,
-                // so the per-channel constants live in registers and the pixel walk needs no division
-                // per-image constants of the (at most 4) patches this slab touches: {mu, 1 / sigma} in float64, Y row of its row 0
-                double *tabd = reinterpret_cast<double *>(bars + 2 * ST + 2 * SB + 2);         // [4][2]
-                int64_t *tabr = reinterpret_cast<int64_t *>(tabd + 8);                           // [4]
-                if (tid < 4) {
-                    const int64_t img = img0 + tid;
-                    double mu = 0.0, inv = 0.0;
-                    int64_t yr = -1;
-                    if (img < ff.n_img) {
-                        mu = (double)ff.mu[img];
-                        inv = 1.0 / (double)ff.sigma[img];
-                        yr = (int64_t)ff.row0[img] - ff.y_f0;
-                    }
-                    tabd[2 * tid] = mu; tabd[2 * tid + 1] = inv; tabr[tid] = yr;
-                }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                const int f_flags = ff.flags;
-                const int jc = tid % cpp, pstep = 128 / cpp;
-                double Sc[4];
-                float eb[4], es1[4], et1[4], es2[4], et2[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int c = jc * 4 + e;
-                    Sc[e] = ff.S[c];
-                    eb[e] = (f_flags & ISS_F_BIAS) ? ff.bias[c] : 0.f;
-                    es1[e] = (f_flags & ISS_F_AFFINE_PRE) ? ff.pre_scale[c] : 1.f;  et1[e] = (f_flags & ISS_F_AFFINE_PRE) ? ff.pre_shift[c] : 0.f;
-                    es2[e] = (f_flags & ISS_F_AFFINE_POST) ? ff.post_scale[c] : 1.f; et2[e] = (f_flags & ISS_F_AFFINE_POST) ? ff.post_shift[c] : 0.f;
-                }
-                const int row_len = a.W * a.C;                   // doubles per Y row
-                // pixel pp = tid / cpp + i * pstep of the slab  <->  (image ti relative to img0, input row ih, column x)
-                // The map Y lives in L2 (shared by ~33 overlapping patches): a dependent load per pixel would serialise
-                // 28 x ~800 cycles of L2 latency per tile, so the loads of FB pixels are issued before any is consumed.
-                constexpr int FB = 8;
-                int pp = tid / cpp;
-                int x = pp % a.W, srow = pp / a.W;
-                const int64_t gfirst = g0 + srow;
-                int ti = (int)(gfirst / a.H - img0);
-                int ih = (int)(gfirst - (gfirst / a.H) * a.H);
-                const int npix = rows * a.W;
-                while (pp < npix) {
-                    double2 ya[FB], yb[FB];
-                    uint32_t dsts[FB];
-                    int tis[FB];
-#pragma unroll
-                    for (int f = 0; f < FB; ++f) {
-                        tis[f] = -1;
-                        dsts[f] = 0;
-                        if (pp < npix) {
-                            dsts[f] = slab_u32 + (uint32_t)pp * pix_bytes + (uint32_t)(((jc & ~7) | ((jc ^ pp) & 7)) << 4);
-                            tis[f] = 4;                          // 4 = zero fill
-                            if (ti < 4 && tabr[ti] >= 0) {
-                                tis[f] = ti;
-                                const double *yp = ff.Y + (tabr[ti] + ih) * (int64_t)row_len + x * a.C + jc * 4;
-                                ya[f] = __ldg(reinterpret_cast<const double2 *>(yp));
-                                yb[f] = __ldg(reinterpret_cast<const double2 *>(yp) + 1);
-                            }
-                            pp += pstep; x += pstep;
-                            while (x >= a.W) { x -= a.W; if (++ih == a.H) { ih = 0; ++ti; } }
-                        }
-                    }
-#pragma unroll
-                    for (int f = 0; f < FB; ++f) {
-                        if (tis[f] < 0) continue;
-                        uint4 wd = make_uint4(0u, 0u, 0u, 0u);
-                        if (tis[f] < 4) {
-                            const double mu = tabd[2 * tis[f]], inv = tabd[2 * tis[f] + 1];
-                            const double yv[4] = {ya[f].x, ya[f].y, yb[f].x, yb[f].y};
-                            uint32_t w4[4];
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                float v = (float)((yv[e] - mu * Sc[e]) * inv) + eb[e];
-                                if (f_flags & ISS_F_AFFINE_PRE) v = fmaf(v, es1[e], et1[e]);
-                                if (f_flags & ISS_F_RELU) v = fmaxf(v, 0.f);
-                                if (f_flags & ISS_F_SIGMOID) v = 1.f / (1.f + expf(-v));
-                                if (f_flags & ISS_F_AFFINE_POST) v = fmaf(v, es2[e], et2[e]);
-                                w4[e] = iss_pack_split(v);
-                            }
-                            wd = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-                        }
-                        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dsts[f]), "r"(wd.x), "r"(wd.y), "r"(wd.z), "r"(wd.w) : "memory");
-                    }
-                }
-            } else {
+            {
                 for (int q = tid; q < total; q += 128) {
                     const uint32_t dst = slab_u32 + (uint32_t)p * pix_bytes + (uint32_t)(((j & ~7) | ((j ^ p) & 7)) << 4);
                     const bool ok = q < avail;
@@ -460,9 +375,7 @@ int launch_tc3h_p(const ConvArgs &a, const F16Args &h, int slab_bytes, cudaStrea
     const int64_t gm = a.slab_tpi > 0 ? (Q / a.OH) * a.slab_tpi : (Q + a.slab_R - 1) / a.slab_R;
     ISS_REQUIRE(gm < (1ll << 31), ISS_ERR_INVALID, "conv_tc_f16: M too large");
     dim3 grid((unsigned)gm, (unsigned)(a.N / BN));
-    FirstFuse ff = {};
-    if (a.first) ff = *a.first;
-    kern<<<grid, Cfg::THREADS, Cfg::FIXED + slab_bytes, st>>>(a, h, ff);
+    kern<<<grid, Cfg::THREADS, Cfg::FIXED + slab_bytes, st>>>(a, h);
     ISS_CUDA_OK(cudaGetLastError());
     iss_count_launch();
     return ISS_OK;
@@ -471,10 +384,7 @@ int launch_tc3h_p(const ConvArgs &a, const F16Args &h, int slab_bytes, cudaStrea
 template <int BN, int SB, int ST>
 int launch_tc3h(const ConvArgs &a, const F16Args &h, int slab_bytes, cudaStream_t st)
 {
-    if (a.first) {
-        ISS_REQUIRE(128 % (a.C / 4) == 0, ISS_ERR_UNSUPPORTED, "conv_tc_f16: fused first layer needs 128 %% (C / 4) == 0");
-        return launch_tc3h_p<BN, SB, ST, IN_FIRST>(a, h, slab_bytes, st);
-    }
+    ISS_REQUIRE(!a.first, ISS_ERR_UNSUPPORTED, "conv_tc_f16: the fused first layer needs the direct kernel");
     return a.in_packed ? launch_tc3h_p<BN, SB, ST, IN_PACKED>(a, h, slab_bytes, st) : launch_tc3h_p<BN, SB, ST, IN_F32>(a, h, slab_bytes, st);
 }
 
