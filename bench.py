@@ -653,13 +653,13 @@ def run_b200(args):
     peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)' if 'bf16_tflops_sustained' in peaks else 'fallback 1.4 PFLOP/s sustained (of fallback)'
     ach = (fl.value / max(nlaunch.value, 1)) / (tms.value / max(nlaunch.value, 1) * 1e-3) / 1e12 if tms.value > 0 else 0.0
     mode = lib.iss_get_gemm_mode()
-    gemm = {0: 'fp32 CUDA cores', 2: 'tcgen05 kind::tf32, 3xTF32 split', 3: 'tcgen05 kind::f16, fp16 hi/lo split (3 products)'}.get(mode, 'engine %d' % mode)
+    gemm = {0: 'fp32 CUDA cores', 2: 'tcgen05 kind::tf32, 3xTF32 split', 3: 'tcgen05 kind::f16 direct kernel (both operands from shared memory), fp16 hi/lo split (3 products), first layer fused into the operand fill'}.get(mode, 'engine %d' % mode)
     traffic, traffic_src = ncu_dram_bytes(dominant_profile(mode))
     roof = {'bound': 'tensor', 'kernel': 'conv_gemm %s (VAD layer %d: %s)' % (gemm, dom, layer_name(seg.vad.nn.lowered.descs[dom])),
             'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf, 'traffic': traffic, 'traffic_source': traffic_src,
             'peak_source': peak_src, 'launches': int(nlaunch.value), 'avg_launch_ms': tms.value / max(nlaunch.value, 1),
             'flops_per_launch': fl.value / max(nlaunch.value, 1), 'share_of_step': tms.value / ms,
-            'note': 'useful fp32-equivalent FLOPs; the tensor pipe executes 3x as many (hi.hi + hi.lo + lo.hi), so the ceiling of this scheme is 1/3'}
+            'note': 'useful fp32-equivalent FLOPs of the layer; the tensor pipe executes 3x as many (hi.hi + hi.lo + lo.hi) on 1/0.773 as many rows (tall-image slots), so the ceiling of this scheme is 0.257; the time includes the fused first layer'}
 
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': warm,
@@ -670,7 +670,7 @@ def run_b200(args):
                    'networks': 'synthetic-weight stand-ins of the ~1.4M-parameter CNN family (release .hdf5 absent)',
                    'fft': args.fft, 'l2': 'inputs larger than L2 (%.2f GB PCM per step)' % (pcm.numel() * 2 / 1e9),
                    'parallelism': ('single GPU' if world == 1 else
-                                   'one %g h recording time-sharded over %d GPUs (34-frame halo); NCCL all-gathers of loge, CNN posteriors, label tracks and (>= 3 ranks) max-plus transfer matrices of the energy Viterbi' % (args.hours * world, world)),
+                                   'one %g h recording time-sharded over %d GPUs (34-frame halo); NCCL all-gathers of loge and of the CNN posteriors, Viterbi passes replicated (bit-identical to one GPU)' % (args.hours * world, world)),
                    'segments': len(segs),
                    'vad_flops_per_patch': seg.vad.nn.flops_per_patch, 'gender_flops_per_patch': seg.gender.nn.flops_per_patch},
         'clocks': clk,
@@ -713,7 +713,7 @@ def run_b200(args):
 
 def dominant_profile(mode):
     """The committed `ncu --set full` summary of the dominant kernel for this engine (per-round file name)."""
-    name = {3: 'r02_conv_gemm_tc3h_full.txt'}.get(mode)
+    name = {3: 'r02_direct_tc4h_full.txt'}.get(mode)
     return os.path.join(ROOT, 'profiles', name) if name else None
 
 
@@ -721,7 +721,7 @@ def kernel_source_hash():
     """sha256 over the sources of the dominant kernel; tools/ncu_summary.py stamps it into the profile summary."""
     import hashlib
     h = hashlib.sha256()
-    for f in ('conv_gemm_tc_f16.cu', 'tc_common.cuh', 'conv_gemm.cuh'):
+    for f in ('conv_gemm_tc_f16d.cu', 'tc_common.cuh', 'conv_gemm.cuh'):
         with open(os.path.join(ROOT, 'inaspeechsegmenter_b200', 'csrc', f), 'rb') as fh:
             h.update(fh.read())
     return h.hexdigest()

@@ -5,6 +5,7 @@ parallelism, what the reference's Pyro4 farm did across hosts)."""
 import argparse
 import glob
 import os
+import sys
 import warnings
 
 description = """Do Speech/Music(/Noise) and Male/Female segmentation and store segmentations into CSV files. Segments labelled 'noEnergy' are discarded from music, noise, speech and gender analysis. 'speech', 'male' and 'female' labels include speech over music and speech over noise. 'music' and 'noise' labels are pure segments that are not supposed to contain speech.
@@ -70,6 +71,9 @@ def main(argv=None):
         procs.append(p)
     for p in procs:
         p.join()
+    failed = [(dev, p.exitcode) for dev, p in zip(devices, procs) if p.exitcode != 0]
+    if failed:                                   # a crashed worker must not look like success to the caller's shell
+        sys.exit('worker(s) failed (device, exit code): %r' % failed)
     return None
 
 

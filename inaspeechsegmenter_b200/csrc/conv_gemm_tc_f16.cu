@@ -464,12 +464,15 @@ int iss_launch_conv_tc_f16(ConvArgs &a, cudaStream_t st)
 int iss_prepare_f16_weights(const float *h_w, int K, int N, void **d_out, float *inv_scale)
 {
     *d_out = nullptr; *inv_scale = 1.f;
-    if (K % HBK != 0 || N % 64 != 0) return ISS_OK;              // not a shape this engine takes
-    std::vector<float> wt((size_t)N * K);                        // transposed [N][K]
+    // K = 32 (a 1x1 convolution / Dense layer over 32 channels) is zero-padded to one 64-wide k-block: only the direct
+    // kernel (conv_gemm_tc_f16d.cu) reads such an image
+    const int Kp = K == 32 ? HBK : K;
+    if (Kp % HBK != 0 || N % 64 != 0) return ISS_OK;             // not a shape this engine takes
+    std::vector<float> wt((size_t)N * Kp, 0.f);                  // transposed [N][Kp]
     for (int k = 0; k < K; ++k)
-        for (int n = 0; n < N; ++n) wt[(size_t)n * K + k] = h_w[(size_t)k * N + n];
+        for (int n = 0; n < N; ++n) wt[(size_t)n * Kp + k] = h_w[(size_t)k * N + n];
     std::vector<__half> img;
-    const float scale = iss_f16_build_image(wt.data(), N, K, K, iss_f16_bn_for(N), img);
+    const float scale = iss_f16_build_image(wt.data(), N, Kp, Kp, iss_f16_bn_for(N), img);
     void *d = nullptr;
     cudaError_t e = cudaMalloc(&d, img.size() * sizeof(__half));
     if (e != cudaSuccess) { iss_set_error("cudaMalloc f16 weights: %s", cudaGetErrorString(e)); return ISS_ERR_NOMEM; }

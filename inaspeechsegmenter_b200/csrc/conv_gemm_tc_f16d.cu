@@ -12,17 +12,23 @@
 // CNNs -- in exchange for deleting the producers' 32 KB of LDS + PRMT + tcgen05.st per k-block, which bounded the
 // TMEM-operand kernel (conv_gemm_tc_f16.cu) at ~36 % of the tensor pipe.
 //
-// One persistent CTA per SM, 448 threads, warp-specialised:
+// One persistent CTA per SM, 512 threads, warp-specialised:
 //   warp 0      MMA issuer (warp-uniform loop, tcgen05 under elect.sync)
 //   warp 1      weight loader: one cp.async.bulk per 16 KB stage [Bh | Bl], 3-deep ring
-//   warps 2-5   epilogue (one TMEM lane quadrant each): accumulators -> bias/BN/ReLU -> split-half words or fp32 -> HBM
-//   warps 6-13  slab fill: de-interleaves split-half words from HBM (IN_PACKED), or takes the 2x2 / stride-2 maximum of
+//   warps 2-5   epilogue (one TMEM lane quadrant each; 2-9 for the residual layers, one per quadrant and sub-tile):
+//               accumulators -> bias/BN (+ residual) / ReLU -> split-half words or fp32 -> HBM
+//   the rest    slab fill: de-interleaves split-half words from HBM (IN_PACKED), or takes the 2x2 / stride-2 maximum of
 //               the un-pooled tensor on the way (IN_POOL: the MaxPooling2D layer in front never runs), or EVALUATES the
 //               one-channel first convolution from the shared two-float map Yh + Yl (IN_FIRST, FirstFuse in conv_gemm.cuh)
 // A tile is DT = 2 sub-tiles of 128 slots that share the slab and every weight stage (half the weight traffic of a
 // 128-row tile); slab and accumulators are double-buffered, so fill(i+1), MMA(i) and epilogue(i-1) overlap.
 // Per k-block (= 64 input channels of one filter tap) and sub-tile: Ah.[Bh | Bl] (N = 128) and Al.Bh (N = 64), as in
 // the other fp16-split kernels; TMEM: 2 buffers x 2 sub-tiles x 128 columns = 512.
+// 1x1 convolutions / Dense layers are the degenerate case (one tap, every slot useful): the kernel then is a persistent
+// GEMM whose A tile (256 rows x C) stays in shared memory for all NT n-tile passes -- used for ResNet101's "expand"
+// convolutions (K = 32 .. 128, N = 128 .. 512, + residual + ReLU), which are memory-bound and ran at ~1/6 of HBM speed as
+// one-tile CTAs of the gather kernel (2 k-blocks of MMAs per CTA, un-overlapped 128 x 128 epilogue).  C = 32 is zero-padded
+// to one 64-channel k-block; the input may be fp32 (IN_F32: split in the fill); the residual may be fp32 or words.
 // Wider layers: C = 64 * CB input channels are CB planes pairs per slab buffer (k-block = (tap, channel block)); N = 64 * NT
 // output channels are NT passes over the SAME slab (pass = (tile, n-tile), accumulators alternate per pass).  When two
 // slab buffers do not fit (C = 128: 139 KB each) the kernel runs with one: the fill of the next tile then waits for the
@@ -43,16 +49,14 @@ constexpr int HBK = 64;
 constexpr int DT = 2;                                   // 128-slot sub-tiles per tile
 constexpr int DSB = 3;                                  // weight stages
 constexpr int DBN = 64;                                 // output channels per pass (n-tile)
-constexpr int D_NMAX = 256;                             // output channels of a layer
-constexpr int D_FILL_WARPS = 8;
-constexpr int D_FILL_THREADS = 32 * D_FILL_WARPS;
-constexpr int D_FIRST_FILL = 6;                         // first fill warp
-constexpr int D_THREADS = 32 * (D_FIRST_FILL + D_FILL_WARPS);
+constexpr int D_NMAX = 512;                             // output channels of a layer
+constexpr int D_WARPS = 16;                             // MMA issuer, weight loader, n_epi epilogue warps (4 or 8), the rest fill the slab
+constexpr int D_THREADS = 32 * D_WARPS;
 constexpr int D_B_STAGE = 2 * DBN * 128;                // [hi rows | lo rows]
 constexpr int D_TAB = 8;                                // images a slab may touch (IN_FIRST table)
 constexpr int D_SMEM_MAX = 232448;
 
-constexpr int DIN_PACKED = 1, DIN_FIRST = 2, DIN_POOL = 3;
+constexpr int DIN_PACKED = 1, DIN_FIRST = 2, DIN_POOL = 3, DIN_F32 = 4;
 
 struct DirectArgs {
     const unsigned char *wt;    // tiled fp16 image [k-block][hi | lo][64 rows x 128 B, SWIZZLE_128B]
@@ -61,9 +65,11 @@ struct DirectArgs {
     int n_tiles;
     int n_img;
     int64_t total_pix;          // n_img * H * W
-    int cb;                     // 64-channel blocks of the input (C / 64), a power of two
+    int cb;                     // 64-channel blocks of the input (ceil(C / 64)), a power of two
+    int c_real;                 // input channels in memory (32 is zero-padded to one block)
     int nt;                     // 64-channel n-tiles (N / 64)
     int bn_img;                 // n-tile width of the weight image (64 or 128, iss_f16_bn_for)
+    int n_epi;                  // epilogue warps: 4 (one per TMEM lane quadrant, both sub-tiles) or 8 (one per quadrant and sub-tile)
 };
 
 __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
@@ -82,12 +88,10 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, ui
 }
 
 struct DSmem {                                           // everything behind the 1024-aligned operand buffers
-    float k1[D_NMAX], k0[D_NMAX], es2[D_NMAX], et2[D_NMAX];   // epilogue: y = acc * k1 + k0, ReLU, y * es2 + et2
     long long tab_row[2][D_TAB];                         // IN_FIRST: Y row of input row 0 of the images a slab touches (-1: none)
     uint64_t slab_full[2], slab_empty[2], acc_full[2], acc_empty[2], b_full[DSB], b_empty[DSB];
     uint32_t tmem_slot;
 };
-
 template <int MODE, int NBUF>
 __global__ void __launch_bounds__(D_THREADS, 1)
 conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d)
@@ -99,6 +103,8 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d)
     unsigned char *slab = smem + DSB * D_B_STAGE;         // [NBUF buffers][channel block][hi plane | lo plane]
     const uint32_t slab_buf = 2u * (uint32_t)d.cb * plane;
     DSmem *sm = reinterpret_cast<DSmem *>(slab + (size_t)NBUF * slab_buf);
+    float *cst = reinterpret_cast<float *>(sm + 1);       // k1 | k0 | es2 | et2, N floats each (y = acc * k1 + k0, ReLU, y * es2 + et2)
+    const int n_fill_warps = D_WARPS - 2 - d.n_epi, first_fill = 2 + d.n_epi, nfill = 32 * n_fill_warps;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nkb = a.KH * a.KW * d.cb;                   // k-block = 64 channels of one filter tap
@@ -106,8 +112,8 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d)
 
     if (tid == 0) {
         for (int b = 0; b < 2; ++b) {
-            mbar_init(&sm->slab_full[b], D_FILL_WARPS); mbar_init(&sm->slab_empty[b], 1);
-            mbar_init(&sm->acc_full[b], 1); mbar_init(&sm->acc_empty[b], 4);
+            mbar_init(&sm->slab_full[b], n_fill_warps); mbar_init(&sm->slab_empty[b], 1);
+            mbar_init(&sm->acc_full[b], 1); mbar_init(&sm->acc_empty[b], d.n_epi);
         }
         for (int s = 0; s < DSB; ++s) { mbar_init(&sm->b_full[s], 1); mbar_init(&sm->b_empty[s], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -116,12 +122,14 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm->tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int n = tid; n < a.N; n += D_THREADS) {          // epilogue constants, once per CTA
-        const bool has_bias = a.flags & ISS_F_BIAS, pre = a.flags & ISS_F_AFFINE_PRE, post = a.flags & ISS_F_AFFINE_POST;
-        const float eb = has_bias ? __ldg(a.bias + n) : 0.f;
-        const float s1 = pre ? __ldg(a.pre_scale + n) : 1.f, t1 = pre ? __ldg(a.pre_shift + n) : 0.f;
-        sm->k1[n] = d.inv_scale * s1; sm->k0[n] = fmaf(eb, s1, t1);
-        sm->es2[n] = post ? __ldg(a.post_scale + n) : 1.f; sm->et2[n] = post ? __ldg(a.post_shift + n) : 0.f;
+    {
+        for (int n = tid; n < a.N; n += D_THREADS) {      // epilogue constants, once per CTA
+            const bool has_bias = a.flags & ISS_F_BIAS, pre = a.flags & ISS_F_AFFINE_PRE, post = a.flags & ISS_F_AFFINE_POST;
+            const float eb = has_bias ? __ldg(a.bias + n) : 0.f;
+            const float s1 = pre ? __ldg(a.pre_scale + n) : 1.f, t1 = pre ? __ldg(a.pre_shift + n) : 0.f;
+            cst[n] = d.inv_scale * s1; cst[a.N + n] = fmaf(eb, s1, t1);
+            cst[2 * a.N + n] = post ? __ldg(a.post_scale + n) : 1.f; cst[3 * a.N + n] = post ? __ldg(a.post_shift + n) : 0.f;
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -207,11 +215,14 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d)
                 }
             }
         }
-    } else if (warp < D_FIRST_FILL) {
+    } else if (warp < first_fill) {
         // ============================ epilogue ============================
         const int quad = warp & 3;                        // the TMEM lanes this warp may read
         const uint32_t lane_addr = ((uint32_t)(quad * 32)) << 16;
-        const bool relu = a.flags & ISS_F_RELU, post = a.flags & ISS_F_AFFINE_POST;
+        const bool relu = a.flags & ISS_F_RELU, post = a.flags & ISS_F_AFFINE_POST, resid = a.flags & ISS_F_RESIDUAL;
+        // 8 epilogue warps: warps 2-5 take sub-tile 0, warps 6-9 sub-tile 1 (twice the loads / stores in flight: the residual
+        // layers are bound by memory latency x bytes in flight, not by instructions)
+        const int t_first = d.n_epi == 8 ? ((warp - 2) >> 2) : 0, t_last = d.n_epi == 8 ? t_first + 1 : DT;
         uint32_t p = 0;
         for (int tile = blockIdx.x; tile < d.n_tiles; tile += gridDim.x) {
             for (int nt = 0; nt < d.nt; ++nt, ++p) {
@@ -221,37 +232,61 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d)
                 tc_fence_after();
                 const int nb = nt * DBN;
 #pragma unroll 1
-                for (int t = 0; t < DT; ++t) {
+                for (int t = t_first; t < t_last; ++t) {
                     const uint32_t slot = (uint32_t)tile * (DT * 128u) + (uint32_t)t * 128u + (uint32_t)(quad * 32 + lane);
                     const uint32_t img = slot / HW, rem = slot - img * HW;
                     const uint32_t oh = rem / (uint32_t)a.W, ow = rem - oh * (uint32_t)a.W;
                     const bool valid = img < (uint32_t)d.n_img && oh < (uint32_t)a.OH && ow < (uint32_t)a.OW;
-                    float *dst = a.out + (((int64_t)img * a.OH + oh) * a.OW + ow) * a.N + nb;
+                    const int64_t orow = (((int64_t)img * a.OH + oh) * a.OW + ow) * a.N + nb;       // of THIS lane's row
+                    if (resid && valid) {                           // the residual of the pass behind this one -> L2 while this one is computed
+                        const float *nx = nt + 1 < d.nt ? a.residual + orow + DBN
+                                                        : a.residual + orow - nb + (int64_t)gridDim.x * (DT * 128) * a.N;     // (1x1 layers: row = slot)
+                        if (nt + 1 < d.nt || (a.KH * a.KW == 1 && tile + (int)gridDim.x < d.n_tiles && (int64_t)slot + (int64_t)gridDim.x * (DT * 128) < a.M)) {
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 32));
+                        }
+                    }
+                    {
+                        float *dst = a.out + orow;
+                        const uint4 *res = resid ? reinterpret_cast<const uint4 *>(a.residual + orow) : nullptr;
 #pragma unroll 1
-                    for (int c = 0; c < DBN; c += 32) {
-                        uint32_t acc[32], corr[32];
-                        const uint32_t col = tmem_base + lane_addr + abuf * 256u + (uint32_t)t * 128u + (uint32_t)c;
-                        tmem_ld32(col, acc);
-                        tmem_ld32(col + DBN, corr);
-                        if (valid) {
+                        for (int c = 0; c < DBN; c += 32) {
+                            uint32_t acc[32];
+                            {
+                                uint32_t corr[32];
+                                const uint32_t col = tmem_base + lane_addr + abuf * 256u + (uint32_t)t * 128u + (uint32_t)c;
+                                tmem_ld32(col, acc);
+                                tmem_ld32(col + DBN, corr);
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                float y[4];
+                                for (int q = 0; q < 32; ++q) acc[q] = __float_as_uint(__uint_as_float(acc[q]) + __uint_as_float(corr[q]));
+                            }
+                            if (valid) {
+                                uint4 rw[8];
+                                if (resid) {
 #pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    const int n = nb + c + 4 * j + q;
-                                    float v = fmaf(__uint_as_float(acc[4 * j + q]) + __uint_as_float(corr[4 * j + q]), sm->k1[n], sm->k0[n]);
-                                    if (relu) v = fmaxf(v, 0.f);
-                                    if (post) v = fmaf(v, sm->es2[n], sm->et2[n]);
-                                    y[q] = v;
+                                    for (int j = 0; j < 8; ++j) rw[j] = __ldg(res + (c >> 2) + j);
                                 }
-                                if (a.out_packed) {
-                                    uint4 w;
-                                    iss_pack_split2(y[0], y[1], w.x, w.y);
-                                    iss_pack_split2(y[2], y[3], w.z, w.w);
-                                    *reinterpret_cast<uint4 *>(dst + c + 4 * j) = w;
-                                } else
-                                    *reinterpret_cast<float4 *>(dst + c + 4 * j) = make_float4(y[0], y[1], y[2], y[3]);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    float y[4];
+                                    const uint32_t r4[4] = {rw[j].x, rw[j].y, rw[j].z, rw[j].w};
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) {
+                                        const int n = nb + c + 4 * j + q;
+                                        float v = fmaf(__uint_as_float(acc[4 * j + q]), cst[n], cst[a.N + n]);
+                                        if (resid) v += a.residual_packed ? iss_unpack_split(r4[q]) : __uint_as_float(r4[q]);
+                                        if (relu) v = fmaxf(v, 0.f);
+                                        if (post) v = fmaf(v, cst[2 * a.N + n], cst[3 * a.N + n]);
+                                        y[q] = v;
+                                    }
+                                    if (a.out_packed) {
+                                        uint4 w;
+                                        iss_pack_split2(y[0], y[1], w.x, w.y);
+                                        iss_pack_split2(y[2], y[3], w.z, w.w);
+                                        *reinterpret_cast<uint4 *>(dst + c + 4 * j) = w;
+                                    } else
+                                        *reinterpret_cast<float4 *>(dst + c + 4 * j) = make_float4(y[0], y[1], y[2], y[3]);
+                                }
                             }
                         }
                     }
@@ -263,7 +298,7 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d)
         }
     } else {
         // ============================ slab fill ============================
-        const int ftid = tid - D_FIRST_FILL * 32;
+        const int ftid = tid - first_fill * 32;
         const int j = ftid & 7;                           // 16-byte chunk = channels 8j .. 8j+7
         // fused first layer: the second affine (behind the ReLU) is per channel; alpha / beta are per (patch, channel)
         float fs2[8], ft2[8];
@@ -289,7 +324,7 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d)
                     const int64_t img = (int64_t)img0 + ftid;
                     sm->tab_row[tbuf][ftid] = img < ff.n_img ? (long long)ff.row0[img] - ff.y_f0 : -1ll;
                 }
-                asm volatile("bar.sync 1, %0;" ::"n"(D_FILL_THREADS) : "memory");
+                asm volatile("bar.sync 1, %0;" ::"r"(nfill) : "memory");
                 const int f_flags = ff.flags;
                 const int64_t row_len = (int64_t)a.W * HBK;            // floats per Y row
                 // this thread's pixels: slab rows (ftid >> 3) + 32 k; (t, ih, x) = image relative to img0, input row, column
@@ -302,7 +337,7 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d)
                 int cur_t = -1;
                 float al[8], bh[8], bl[8];                              // alpha, beta_hi, beta_lo of image cur_t, channels 8j..8j+7
                 constexpr int FB = 2;                                   // pixels whose loads are in flight together
-                constexpr int PSTEP = D_FILL_THREADS / 8;
+                const int PSTEP = nfill >> 3;
                 for (int pl0 = ftid >> 3; pl0 < d.npix; pl0 += FB * PSTEP) {
                     float4 yh[FB][2], yl[FB][2];
                     int ti[FB];
@@ -369,12 +404,12 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d)
                 const int cshift = 3 + (d.cb == 1 ? 0 : d.cb == 2 ? 1 : 2), cpp = 1 << cshift;
                 const int total = d.npix << cshift;
                 constexpr int FB = 2;                                   // tasks whose 8 loads each are in flight together (HBM latency)
-                for (int idx0 = ftid; idx0 < total; idx0 += FB * D_FILL_THREADS) {
+                for (int idx0 = ftid; idx0 < total; idx0 += FB * nfill) {
                     uint4 u[FB][8];
                     bool live[FB];
 #pragma unroll
                     for (int f = 0; f < FB; ++f) {
-                        const int idx = idx0 + f * D_FILL_THREADS;
+                        const int idx = idx0 + f * nfill;
                         const int pl = idx >> cshift, jj = idx & (cpp - 1);
                         const uint32_t gp = s0 + (uint32_t)pl;
                         live[f] = idx < total && (int64_t)gp < d.total_pix;
@@ -389,7 +424,7 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d)
                     }
 #pragma unroll
                     for (int f = 0; f < FB; ++f) {
-                        const int idx = idx0 + f * D_FILL_THREADS;
+                        const int idx = idx0 + f * nfill;
                         if (idx >= total) continue;
                         const int pl = idx >> cshift, jj = idx & (cpp - 1);
                         uint32_t bw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
@@ -412,35 +447,53 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d)
                     }
                 }
             } else {
-                // task = (pixel pl, chunk jj of 8 channels): two 16-byte loads of split-half words -> one 16-byte chunk of the
-                // hi plane and one of the lo plane of channel block jj >> 3
+                // task = (pixel pl, chunk jj of 8 channels): two 16-byte loads (split-half words, or fp32 values split here)
+                // -> one 16-byte chunk of the hi plane and one of the lo plane of channel block jj >> 3; chunks past the
+                // real channel count (C = 32 padded to 64) are zero
                 const uint4 *src = reinterpret_cast<const uint4 *>(a.in);
                 const int cshift = 3 + (d.cb == 1 ? 0 : d.cb == 2 ? 1 : 2), cpp = 1 << cshift;      // chunks per pixel
+                const int creal = d.c_real >> 3, q4 = d.c_real >> 2;                                // real chunks / uint4 per pixel
                 const int total = d.npix << cshift;
                 constexpr int FB = 4;                                   // tasks whose loads are in flight together
-                for (int idx0 = ftid; idx0 < total; idx0 += FB * D_FILL_THREADS) {
+                for (int idx0 = ftid; idx0 < total; idx0 += FB * nfill) {
                     uint4 u0[FB], u1[FB];
 #pragma unroll
                     for (int f = 0; f < FB; ++f) {
-                        const int idx = idx0 + f * D_FILL_THREADS;
+                        const int idx = idx0 + f * nfill;
                         u0[f] = make_uint4(0u, 0u, 0u, 0u); u1[f] = u0[f];
                         if (idx < total) {
                             const int pl = idx >> cshift, jj = idx & (cpp - 1);
                             const int64_t gp = (int64_t)s0 + pl;
-                            if (gp < d.total_pix) {
-                                const uint4 *p = src + gp * (2 * cpp) + jj * 2;
+                            if (gp < d.total_pix && jj < creal) {
+                                const uint4 *p = src + gp * q4 + jj * 2;
                                 u0[f] = __ldg(p); u1[f] = __ldg(p + 1);
                             }
                         }
                     }
 #pragma unroll
                     for (int f = 0; f < FB; ++f) {
-                        const int idx = idx0 + f * D_FILL_THREADS;
+                        const int idx = idx0 + f * nfill;
                         if (idx >= total) continue;
                         const int pl = idx >> cshift, jj = idx & (cpp - 1);
                         const uint32_t dst = hi_base + (uint32_t)(jj >> 3) * 2u * plane + (uint32_t)pl * 128u + (uint32_t)(((jj & 7) ^ (pl & 7)) << 4);
-                        sts128(dst, __byte_perm(u0[f].x, u0[f].y, 0x5410), __byte_perm(u0[f].z, u0[f].w, 0x5410), __byte_perm(u1[f].x, u1[f].y, 0x5410), __byte_perm(u1[f].z, u1[f].w, 0x5410));
-                        sts128(dst + plane, __byte_perm(u0[f].x, u0[f].y, 0x7632), __byte_perm(u0[f].z, u0[f].w, 0x7632), __byte_perm(u1[f].x, u1[f].y, 0x7632), __byte_perm(u1[f].z, u1[f].w, 0x7632));
+                        if constexpr (MODE == DIN_F32) {
+                            const uint32_t w8[8] = {u0[f].x, u0[f].y, u0[f].z, u0[f].w, u1[f].x, u1[f].y, u1[f].z, u1[f].w};
+                            uint32_t hw[4], lw[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {               // hi = fp16(v), lo = fp16(v - hi): two channels per word
+                                const float v0 = __uint_as_float(w8[2 * e]), v1 = __uint_as_float(w8[2 * e + 1]);
+                                const __half2 hh = __floats2half2_rn(v0, v1);
+                                const float2 hf = __half22float2(hh);
+                                const __half2 ll = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+                                hw[e] = *reinterpret_cast<const uint32_t *>(&hh);
+                                lw[e] = *reinterpret_cast<const uint32_t *>(&ll);
+                            }
+                            sts128(dst, hw[0], hw[1], hw[2], hw[3]);
+                            sts128(dst + plane, lw[0], lw[1], lw[2], lw[3]);
+                        } else {
+                            sts128(dst, __byte_perm(u0[f].x, u0[f].y, 0x5410), __byte_perm(u0[f].z, u0[f].w, 0x5410), __byte_perm(u1[f].x, u1[f].y, 0x5410), __byte_perm(u1[f].z, u1[f].w, 0x5410));
+                            sts128(dst + plane, __byte_perm(u0[f].x, u0[f].y, 0x7632), __byte_perm(u0[f].z, u0[f].w, 0x7632), __byte_perm(u1[f].x, u1[f].y, 0x7632), __byte_perm(u1[f].z, u1[f].w, 0x7632));
+                        }
                     }
                 }
             }
@@ -462,17 +515,29 @@ int direct_npix(const ConvArgs &a)
     return (npix + 7) & ~7;
 }
 
+int direct_cb(const ConvArgs &a) { return (a.C + HBK - 1) / HBK; }
+
 size_t direct_smem(const ConvArgs &a, int nbuf)
 {
-    return (size_t)DSB * D_B_STAGE + (size_t)nbuf * 2 * (a.C / HBK) * direct_npix(a) * 128 + sizeof(DSmem) + 1024;
+    return (size_t)DSB * D_B_STAGE + (size_t)nbuf * 2 * direct_cb(a) * direct_npix(a) * 128 + sizeof(DSmem) + 1024 + (size_t)4 * a.N * sizeof(float);
+}
+
+// slab buffers: two when they fit (fill of tile i+1 under the MMAs of tile i); one is accepted only when a tile has >= 4
+// n-tile passes to amortise the exposed fill (on the 3x3 128 -> 128 layer, 2 passes, one buffer measured slower than
+// the TMEM-operand slab kernel: 286 vs 208 us)
+int direct_nbuf(const ConvArgs &a)
+{
+    if (direct_smem(a, 2) <= (size_t)D_SMEM_MAX) return 2;
+    if (direct_smem(a, 1) <= (size_t)D_SMEM_MAX && a.N / DBN >= 4) return 1;
+    return 0;
 }
 
 template <int MODE, int NBUF>
-int launch_tc4h(const ConvArgs &a, const FirstFuse &ff, const DirectArgs &d, unsigned grid, size_t smem, cudaStream_t st)
+int launch_tc4h(const ConvArgs &a, const FirstFuse &ff, const DirectArgs &d, unsigned grid, cudaStream_t st)
 {
     auto kern = conv_gemm_tc4h_kernel<MODE, NBUF>;
     ISS_CUDA_OK(iss_optin_smem(reinterpret_cast<const void *>(kern), D_SMEM_MAX));
-    kern<<<grid, D_THREADS, smem, st>>>(a, ff, d);
+    kern<<<grid, D_THREADS, direct_smem(a, NBUF), st>>>(a, ff, d);
     ISS_CUDA_OK(cudaGetLastError());
     iss_count_launch();
     return ISS_OK;
@@ -480,27 +545,26 @@ int launch_tc4h(const ConvArgs &a, const FirstFuse &ff, const DirectArgs &d, uns
 
 }  // namespace
 
-// Does the direct kernel take this layer?  Un-padded stride-1 KHxKW convolution with C in {64, 128, 256} input and
-// N = 64 .. 256 (multiple of 64) output channels, input either split-half words or (C = 64) the fused first layer.
-// ISS_B200_F16_DIRECT=0 turns it off (A/B runs against the TMEM-operand slab kernel).
+// Does the direct kernel take this layer?  Un-padded stride-1 KHxKW convolution (1x1 / Dense included) with C in {64, 128,
+// 256} input channels (1x1 also C = 32, zero-padded to one k-block) and N = 64 .. 512 (multiple of 64) output channels;
+// input split-half words, fp32, or (C = 64) the fused first layer; optional residual.
+// ISS_B200_F16_DIRECT=0 turns it off (A/B runs against the TMEM-operand kernels).
 bool iss_conv_f16_direct_covers(const ConvArgs &a)
 {
-    static const bool off = [] { const char *e = getenv("ISS_B200_F16_DIRECT"); return e && e[0] == '0'; }();
-    if (off) return false;
-    if (!a.wt_f16 || a.SH != 1 || a.SW != 1 || a.PT != 0 || a.PL != 0 || a.KH * a.KW <= 1) return false;
+    const char *env = getenv("ISS_B200_F16_DIRECT");                     // read per call: the GPU tests toggle it
+    if (env && env[0] == '0') return false;
+    if (!a.wt_f16 || a.SH != 1 || a.SW != 1 || a.PT != 0 || a.PL != 0) return false;
     if (a.OH != a.H - a.KH + 1 || a.OW != a.W - a.KW + 1 || a.Kp != a.K) return false;
-    if (a.N % DBN != 0 || a.N > D_NMAX || (a.C != 64 && a.C != 128 && a.C != 256) || a.K != a.KH * a.KW * a.C) return false;
-    if (a.flags & (ISS_F_SIGMOID | ISS_F_RESIDUAL)) return false;
-    if (!a.first && !a.in_packed) return false;
-    if (a.first && (a.C != HBK || a.pool_h > 0)) return false;
-    if (a.pool_h > 0 && (a.pool_h / 2 != a.H || a.pool_w / 2 != a.W)) return false;       // fused 2x2 / stride-2 'valid' pooling only
+    const bool c_ok = a.C == 64 || a.C == 128 || a.C == 256 || (a.C == 32 && a.KH * a.KW == 1);
+    if (a.N % DBN != 0 || a.N > D_NMAX || !c_ok || a.K != a.KH * a.KW * a.C) return false;
+    if (a.flags & ISS_F_SIGMOID) return false;
+    if (a.first && (a.C != HBK || a.pool_h > 0 || (a.flags & ISS_F_RESIDUAL))) return false;
+    if (a.pool_h > 0 && (!a.in_packed || a.pool_h / 2 != a.H || a.pool_w / 2 != a.W)) return false;   // fused 2x2 / stride-2 'valid' pooling only
     const int64_t n_img = a.M / ((int64_t)a.OH * a.OW);
     if (n_img * a.H * a.W >= (1ll << 31) - 4096) return false;
     // the IN_FIRST table covers D_TAB images per slab
-    if ((direct_npix(a) - 1) / (a.H * a.W) + 2 > D_TAB) return false;
-    // one slab buffer (NBUF = 1) works but serialises fill and MMA: measured slower than the TMEM-operand slab kernel on the
-    // 3x3 128 -> 128 layer (286 vs 208 us), so the layer is only taken when both buffers fit
-    return direct_smem(a, 2) <= (size_t)D_SMEM_MAX;
+    if (a.first && (direct_npix(a) - 1) / (a.H * a.W) + 2 > D_TAB) return false;
+    return direct_nbuf(a) > 0;
 }
 
 // Returns 1 when the layer is not covered (caller continues with the other fp16-split kernels).
@@ -513,23 +577,25 @@ int iss_launch_conv_tc_f16d(ConvArgs &a, cudaStream_t st)
     d.npix = direct_npix(a);
     d.n_img = (int)(a.M / ((int64_t)a.OH * a.OW));
     d.total_pix = (int64_t)d.n_img * a.H * a.W;
-    d.cb = a.C / HBK;
+    d.cb = direct_cb(a);
+    d.c_real = a.C;
     d.nt = a.N / DBN;
     d.bn_img = iss_f16_bn_for(a.N);                                      // tiling of the weight image (iss_prepare_f16_weights)
+    const char *nepi_env = getenv("ISS_B200_NEPI");                      // A/B runs: 4 or 8
+    d.n_epi = nepi_env ? (atoi(nepi_env) == 8 ? 8 : 4) : ((a.flags & ISS_F_RESIDUAL) ? 8 : 4);
     const int64_t total_slots = ((int64_t)(d.n_img - 1) * a.H + a.OH - 1) * a.W + a.OW;
     d.n_tiles = (int)((total_slots + DT * 128 - 1) / (DT * 128));
     int dev = 0, sms = 0;
     ISS_CUDA_OK(cudaGetDevice(&dev));
     ISS_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const unsigned grid = (unsigned)(d.n_tiles < sms ? d.n_tiles : sms);
-    const bool two = direct_smem(a, 2) <= (size_t)D_SMEM_MAX;
-    const size_t smem = direct_smem(a, two ? 2 : 1);
+    const bool two = direct_nbuf(a) == 2;
     FirstFuse ff = {};
     if (a.first) {
         ff = *a.first;
-        return two ? launch_tc4h<DIN_FIRST, 2>(a, ff, d, grid, smem, st) : launch_tc4h<DIN_FIRST, 1>(a, ff, d, grid, smem, st);
+        return two ? launch_tc4h<DIN_FIRST, 2>(a, ff, d, grid, st) : launch_tc4h<DIN_FIRST, 1>(a, ff, d, grid, st);
     }
-    if (a.pool_h > 0)
-        return two ? launch_tc4h<DIN_POOL, 2>(a, ff, d, grid, smem, st) : launch_tc4h<DIN_POOL, 1>(a, ff, d, grid, smem, st);
-    return two ? launch_tc4h<DIN_PACKED, 2>(a, ff, d, grid, smem, st) : launch_tc4h<DIN_PACKED, 1>(a, ff, d, grid, smem, st);
+    if (a.pool_h > 0) return two ? launch_tc4h<DIN_POOL, 2>(a, ff, d, grid, st) : launch_tc4h<DIN_POOL, 1>(a, ff, d, grid, st);
+    if (!a.in_packed) return two ? launch_tc4h<DIN_F32, 2>(a, ff, d, grid, st) : launch_tc4h<DIN_F32, 1>(a, ff, d, grid, st);
+    return two ? launch_tc4h<DIN_PACKED, 2>(a, ff, d, grid, st) : launch_tc4h<DIN_PACKED, 1>(a, ff, d, grid, st);
 }

@@ -78,7 +78,6 @@ def feats_from_signal(sig, device=0, fft_precision=_lib.FFT_FP64, ctx_name='feat
         warnings.warn("media %s duration is short. Robust results require length of at least 720 milliseconds" % medianame)
         fill = mspec.min() if mspec.numel() else torch.tensor(float('nan'), device=dev)
         mspec = torch.cat((mspec, fill.expand(difflen, 24).to(mspec.dtype)))
-    loge._iss_stats = stats
     return mspec, loge, difflen
 
 
@@ -217,9 +216,7 @@ class Segmenter:
         if isinstance(loge, np.ndarray):
             host = np.ascontiguousarray(loge, dtype=np.float32)
             loge = torch.from_numpy(host).to(self.ctx.device)
-        stats = getattr(loge, '_iss_stats', None)
-        if stats is None:
-            stats = engine.loge_stats(self.ctx, loge)          # same reduction kernel/order as the fused one in K1
+        stats = engine.loge_stats(self.ctx, loge)              # {sum, count} of finite loge: two tiny kernels, fixed order
         track = engine.energy_viterbi(self.ctx, loge, stats, self.energy_ratio, out_stride=2).cpu().numpy()
         return [('noEnergy' if lab == 0 else 'energy', a, b) for lab, a, b in _rle(track)]
 

@@ -285,6 +285,40 @@ def test_k2_first_layer_fused_vs_standalone_and_fallback(rt, synth_models, monke
     monkeypatch.delenv('ISS_B200_FUSE_FIRST', raising=False)
 
 
+@pytest.mark.parametrize('which,nmel', [('smn', 21), ('gender', 24)])
+def test_k2_direct_kernel_variants_vs_oracle(rt, synth_models, monkeypatch, which, nmel):
+    """The direct convolution kernel (both tcgen05 operands from shared memory: fused first layer, 2x2 max-pooling folded
+    into the slab fill) against its fall-backs -- pooling as its own kernel, the TMEM-operand slab kernel -- and the
+    oracle, on ranges that make tiles straddle patches and end in a partial tile."""
+    from oracle import sidekit_oracle as sk
+    cfg, w = synth_models[which]
+    sig = synth_audio(100, seed=9).astype(np.float32) / np.float32(32768)
+    mspec, loge = sk.logmel_loge(sig)
+    P = (len(loge) + 1) // 2
+    net = rt['engine'].CnnModel.from_keras(rt['ctx'], cfg, w, nmel)
+    dm = torch.from_numpy(mspec).cuda()
+    lib = rt['lib'].load()
+    ranges = [(0, 1), (5, 612), (700, P)]
+    ref = _oracle_probs(cfg, w, mspec, nmel, ranges)
+    out, launches = {}, {}
+    for name, env in (('direct', {}), ('pool_kernel', {'ISS_B200_FUSE_POOL': '0'}), ('tmem_operand', {'ISS_B200_F16_DIRECT': '0'})):
+        for k in ('ISS_B200_FUSE_POOL', 'ISS_B200_F16_DIRECT'):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        l0 = lib.iss_launch_count()
+        out[name] = net.forward(dm, ranges).cpu().numpy()
+        launches[name] = lib.iss_launch_count() - l0
+    for k in ('ISS_B200_FUSE_POOL', 'ISS_B200_F16_DIRECT'):
+        monkeypatch.delenv(k, raising=False)
+    for name, got in out.items():
+        assert np.abs(got - ref).max() <= 1e-4, name
+    assert np.abs(out['direct'] - out['pool_kernel']).max() == 0.0          # the fused pooling keeps the same words
+    assert np.abs(out['direct'] - out['tmem_operand']).max() <= 2e-5
+    assert launches['direct'] < launches['pool_kernel']
+    REPORT['k2_direct_variants_%s' % which] = dict(vs_oracle={k: float(np.abs(v - ref).max()) for k, v in out.items()}, launches=launches)
+
+
 @pytest.mark.parametrize('L', [68, 69, 70, 101, 135, 136])
 def test_k2_edge_replication(rt, synth_models, L):
     cfg, w = synth_models['sm']
