@@ -261,31 +261,32 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d)
                                 for (int q = 0; q < 32; ++q) acc[q] = __float_as_uint(__uint_as_float(acc[q]) + __uint_as_float(corr[q]));
                             }
                             if (valid) {
-                                uint4 rw[8];
+                                u32x8 rw[4];                         // 32 channels of residual: four 32-byte loads
                                 if (resid) {
 #pragma unroll
-                                    for (int j = 0; j < 8; ++j) rw[j] = __ldg(res + (c >> 2) + j);
+                                    for (int j = 0; j < 4; ++j) rw[j] = ldg256(res + (c >> 2) + 2 * j);
                                 }
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    float y[4];
-                                    const uint32_t r4[4] = {rw[j].x, rw[j].y, rw[j].z, rw[j].w};
+                                for (int j = 0; j < 4; ++j) {
+                                    float y[8];
 #pragma unroll
-                                    for (int q = 0; q < 4; ++q) {
-                                        const int n = nb + c + 4 * j + q;
-                                        float v = fmaf(__uint_as_float(acc[4 * j + q]), cst[n], cst[a.N + n]);
-                                        if (resid) v += a.residual_packed ? iss_unpack_split(r4[q]) : __uint_as_float(r4[q]);
+                                    for (int q = 0; q < 8; ++q) {
+                                        const int n = nb + c + 8 * j + q;
+                                        float v = fmaf(__uint_as_float(acc[8 * j + q]), cst[n], cst[a.N + n]);
+                                        if (resid) v += a.residual_packed ? iss_unpack_split(rw[j].v[q]) : __uint_as_float(rw[j].v[q]);
                                         if (relu) v = fmaxf(v, 0.f);
                                         if (post) v = fmaf(v, cst[2 * a.N + n], cst[3 * a.N + n]);
                                         y[q] = v;
                                     }
+                                    u32x8 w;
                                     if (a.out_packed) {
-                                        uint4 w;
-                                        iss_pack_split2(y[0], y[1], w.x, w.y);
-                                        iss_pack_split2(y[2], y[3], w.z, w.w);
-                                        *reinterpret_cast<uint4 *>(dst + c + 4 * j) = w;
-                                    } else
-                                        *reinterpret_cast<float4 *>(dst + c + 4 * j) = make_float4(y[0], y[1], y[2], y[3]);
+#pragma unroll
+                                        for (int q = 0; q < 4; ++q) iss_pack_split2(y[2 * q], y[2 * q + 1], w.v[2 * q], w.v[2 * q + 1]);
+                                    } else {
+#pragma unroll
+                                        for (int q = 0; q < 8; ++q) w.v[q] = __float_as_uint(y[q]);
+                                    }
+                                    stg256(dst + c + 8 * j, w);
                                 }
                             }
                         }
@@ -339,7 +340,7 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d)
                 constexpr int FB = 2;                                   // pixels whose loads are in flight together
                 const int PSTEP = nfill >> 3;
                 for (int pl0 = ftid >> 3; pl0 < d.npix; pl0 += FB * PSTEP) {
-                    float4 yh[FB][2], yl[FB][2];
+                    u32x8 yh[FB], yl[FB];
                     int ti[FB];
 #pragma unroll
                     for (int f = 0; f < FB; ++f) {
@@ -349,8 +350,7 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d)
                             if (t < (uint32_t)D_TAB && sm->tab_row[tbuf][t] >= 0) {
                                 ti[f] = (int)t;
                                 const int64_t o = (sm->tab_row[tbuf][t] + ih) * row_len + x * HBK + j * 8;
-                                const float4 *ph = reinterpret_cast<const float4 *>(ff.Yh + o), *pq = reinterpret_cast<const float4 *>(ff.Yl + o);
-                                yh[f][0] = __ldg(ph); yh[f][1] = __ldg(ph + 1); yl[f][0] = __ldg(pq); yl[f][1] = __ldg(pq + 1);
+                                yh[f] = ldg256(ff.Yh + o); yl[f] = ldg256(ff.Yl + o);
                             }
                             x += PSTEP;
                             while (x >= (uint32_t)a.W) { x -= (uint32_t)a.W; if (++ih == (uint32_t)a.H) { ih = 0; ++t; } }
@@ -373,12 +373,10 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d)
                                     bl[4 * q] = vl.x; bl[4 * q + 1] = vl.y; bl[4 * q + 2] = vl.z; bl[4 * q + 3] = vl.w;
                                 }
                             }
-                            const float y8h[8] = {yh[f][0].x, yh[f][0].y, yh[f][0].z, yh[f][0].w, yh[f][1].x, yh[f][1].y, yh[f][1].z, yh[f][1].w};
-                            const float y8l[8] = {yl[f][0].x, yl[f][0].y, yl[f][0].z, yl[f][0].w, yl[f][1].x, yl[f][1].y, yl[f][1].z, yl[f][1].w};
                             float v[8];
 #pragma unroll
                             for (int e = 0; e < 8; ++e) {
-                                float u = fmaf(y8h[e], al[e], bh[e]) + fmaf(y8l[e], al[e], bl[e]);
+                                float u = fmaf(__uint_as_float(yh[f].v[e]), al[e], bh[e]) + fmaf(__uint_as_float(yl[f].v[e]), al[e], bl[e]);
                                 if (f_flags & ISS_F_RELU) u = fmaxf(u, 0.f);
                                 if (f_flags & ISS_F_AFFINE_POST) u = fmaf(u, fs2[e], ft2[e]);
                                 v[e] = u;
@@ -405,7 +403,7 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d)
                 const int total = d.npix << cshift;
                 constexpr int FB = 2;                                   // tasks whose 8 loads each are in flight together (HBM latency)
                 for (int idx0 = ftid; idx0 < total; idx0 += FB * nfill) {
-                    uint4 u[FB][8];
+                    u32x8 u[FB][4];                                     // the 2x2 window: 8 channels (32 bytes) of each pixel
                     bool live[FB];
 #pragma unroll
                     for (int f = 0; f < FB; ++f) {
@@ -418,8 +416,7 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d)
                             const uint32_t ih = rem / (uint32_t)a.W, x = rem - ih * (uint32_t)a.W;
                             const uint4 *p00 = src + (((int64_t)img * a.pool_h + 2 * ih) * a.pool_w + 2 * x) * (2 * cpp) + jj * 2;
                             const uint4 *p10 = p00 + (int64_t)a.pool_w * (2 * cpp);
-                            u[f][0] = __ldg(p00); u[f][1] = __ldg(p00 + 1); u[f][2] = __ldg(p00 + 2 * cpp); u[f][3] = __ldg(p00 + 2 * cpp + 1);
-                            u[f][4] = __ldg(p10); u[f][5] = __ldg(p10 + 1); u[f][6] = __ldg(p10 + 2 * cpp); u[f][7] = __ldg(p10 + 2 * cpp + 1);
+                            u[f][0] = ldg256(p00); u[f][1] = ldg256(p00 + 2 * cpp); u[f][2] = ldg256(p10); u[f][3] = ldg256(p10 + 2 * cpp);
                         }
                     }
 #pragma unroll
@@ -432,12 +429,10 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d)
                             float bv[8];
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {               // window order (0,0) (0,1) (1,0) (1,1), as the pooling kernel
-                                const uint32_t w8[8] = {u[f][2 * q].x, u[f][2 * q].y, u[f][2 * q].z, u[f][2 * q].w,
-                                                        u[f][2 * q + 1].x, u[f][2 * q + 1].y, u[f][2 * q + 1].z, u[f][2 * q + 1].w};
 #pragma unroll
                                 for (int e = 0; e < 8; ++e) {
-                                    const float fv = iss_unpack_split(w8[e]);
-                                    if (q == 0 || fv > bv[e] || fv != fv) { bv[e] = fv; bw[e] = w8[e]; }
+                                    const float fv = iss_unpack_split(u[f][q].v[e]);
+                                    if (q == 0 || fv > bv[e] || fv != fv) { bv[e] = fv; bw[e] = u[f][q].v[e]; }
                                 }
                             }
                         }
@@ -456,18 +451,16 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d)
                 const int total = d.npix << cshift;
                 constexpr int FB = 4;                                   // tasks whose loads are in flight together
                 for (int idx0 = ftid; idx0 < total; idx0 += FB * nfill) {
-                    uint4 u0[FB], u1[FB];
+                    u32x8 u[FB];
 #pragma unroll
                     for (int f = 0; f < FB; ++f) {
                         const int idx = idx0 + f * nfill;
-                        u0[f] = make_uint4(0u, 0u, 0u, 0u); u1[f] = u0[f];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) u[f].v[e] = 0u;
                         if (idx < total) {
                             const int pl = idx >> cshift, jj = idx & (cpp - 1);
                             const int64_t gp = (int64_t)s0 + pl;
-                            if (gp < d.total_pix && jj < creal) {
-                                const uint4 *p = src + gp * q4 + jj * 2;
-                                u0[f] = __ldg(p); u1[f] = __ldg(p + 1);
-                            }
+                            if (gp < d.total_pix && jj < creal) u[f] = ldg256(src + gp * q4 + jj * 2);
                         }
                     }
 #pragma unroll
@@ -477,11 +470,10 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d)
                         const int pl = idx >> cshift, jj = idx & (cpp - 1);
                         const uint32_t dst = hi_base + (uint32_t)(jj >> 3) * 2u * plane + (uint32_t)pl * 128u + (uint32_t)(((jj & 7) ^ (pl & 7)) << 4);
                         if constexpr (MODE == DIN_F32) {
-                            const uint32_t w8[8] = {u0[f].x, u0[f].y, u0[f].z, u0[f].w, u1[f].x, u1[f].y, u1[f].z, u1[f].w};
                             uint32_t hw[4], lw[4];
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {               // hi = fp16(v), lo = fp16(v - hi): two channels per word
-                                const float v0 = __uint_as_float(w8[2 * e]), v1 = __uint_as_float(w8[2 * e + 1]);
+                                const float v0 = __uint_as_float(u[f].v[2 * e]), v1 = __uint_as_float(u[f].v[2 * e + 1]);
                                 const __half2 hh = __floats2half2_rn(v0, v1);
                                 const float2 hf = __half22float2(hh);
                                 const __half2 ll = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
@@ -491,8 +483,8 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d)
                             sts128(dst, hw[0], hw[1], hw[2], hw[3]);
                             sts128(dst + plane, lw[0], lw[1], lw[2], lw[3]);
                         } else {
-                            sts128(dst, __byte_perm(u0[f].x, u0[f].y, 0x5410), __byte_perm(u0[f].z, u0[f].w, 0x5410), __byte_perm(u1[f].x, u1[f].y, 0x5410), __byte_perm(u1[f].z, u1[f].w, 0x5410));
-                            sts128(dst + plane, __byte_perm(u0[f].x, u0[f].y, 0x7632), __byte_perm(u0[f].z, u0[f].w, 0x7632), __byte_perm(u1[f].x, u1[f].y, 0x7632), __byte_perm(u1[f].z, u1[f].w, 0x7632));
+                            sts128(dst, __byte_perm(u[f].v[0], u[f].v[1], 0x5410), __byte_perm(u[f].v[2], u[f].v[3], 0x5410), __byte_perm(u[f].v[4], u[f].v[5], 0x5410), __byte_perm(u[f].v[6], u[f].v[7], 0x5410));
+                            sts128(dst + plane, __byte_perm(u[f].v[0], u[f].v[1], 0x7632), __byte_perm(u[f].v[2], u[f].v[3], 0x7632), __byte_perm(u[f].v[4], u[f].v[5], 0x7632), __byte_perm(u[f].v[6], u[f].v[7], 0x7632));
                         }
                     }
                 }

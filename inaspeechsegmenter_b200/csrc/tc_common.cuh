@@ -110,6 +110,22 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
         : "memory");
 }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): when every lane touches its own line, a 32-byte access per lane
+// moves a whole sector per request instead of half of one -- half the LSU requests of two 16-byte accesses
+struct __align__(32) u32x8 { uint32_t v[8]; };
+__device__ __forceinline__ u32x8 ldg256(const void *p)
+{
+    u32x8 r;
+    asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg256(void *p, const u32x8 &r)
+{
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "r"(r.v[0]), "r"(r.v[1]), "r"(r.v[2]), "r"(r.v[3]), "r"(r.v[4]), "r"(r.v[5]), "r"(r.v[6]), "r"(r.v[7]) : "memory");
+}
+
 constexpr uint32_t tmem_cols_pow2(uint32_t n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
 
 __device__ __forceinline__ void cp_async16(void *dst, const void *src, int src_bytes)
