@@ -466,13 +466,15 @@ int iss_prepare_f16_weights(const float *h_w, int K, int N, void **d_out, float 
     *d_out = nullptr; *inv_scale = 1.f;
     // K = 32 (a 1x1 convolution / Dense layer over 32 channels) is zero-padded to one 64-wide k-block: only the direct
     // kernel (conv_gemm_tc_f16d.cu) reads such an image
+    // (likewise N = 32 is padded with zero rows to one 64-wide n-tile)
     const int Kp = K == 32 ? HBK : K;
-    if (Kp % HBK != 0 || N % 64 != 0) return ISS_OK;             // not a shape this engine takes
-    std::vector<float> wt((size_t)N * Kp, 0.f);                  // transposed [N][Kp]
+    const int Np = N == 32 ? 64 : N;
+    if (Kp % HBK != 0 || Np % 64 != 0) return ISS_OK;            // not a shape this engine takes
+    std::vector<float> wt((size_t)Np * Kp, 0.f);                 // transposed [Np][Kp]
     for (int k = 0; k < K; ++k)
         for (int n = 0; n < N; ++n) wt[(size_t)n * Kp + k] = h_w[(size_t)k * N + n];
     std::vector<__half> img;
-    const float scale = iss_f16_build_image(wt.data(), N, Kp, Kp, iss_f16_bn_for(N), img);
+    const float scale = iss_f16_build_image(wt.data(), Np, Kp, Kp, iss_f16_bn_for(Np), img);
     void *d = nullptr;
     cudaError_t e = cudaMalloc(&d, img.size() * sizeof(__half));
     if (e != cudaSuccess) { iss_set_error("cudaMalloc f16 weights: %s", cudaGetErrorString(e)); return ISS_ERR_NOMEM; }

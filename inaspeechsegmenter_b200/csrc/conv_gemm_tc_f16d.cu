@@ -250,7 +250,7 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d)
                         float *dst = a.out + orow;
                         const uint4 *res = resid ? reinterpret_cast<const uint4 *>(a.residual + orow) : nullptr;
 #pragma unroll 1
-                        for (int c = 0; c < DBN; c += 32) {
+                        for (int c = 0; c < DBN && nb + c < a.N; c += 32) {       // (N = 32: only the first 32 columns exist)
                             uint32_t acc[32];
                             {
                                 uint32_t corr[32];
@@ -520,7 +520,7 @@ size_t direct_smem(const ConvArgs &a, int nbuf)
 int direct_nbuf(const ConvArgs &a)
 {
     if (direct_smem(a, 2) <= (size_t)D_SMEM_MAX) return 2;
-    if (direct_smem(a, 1) <= (size_t)D_SMEM_MAX && a.N / DBN >= 4) return 1;
+    if (direct_smem(a, 1) <= (size_t)D_SMEM_MAX && (a.N / DBN >= 4 || a.KH * a.KW == 1)) return 1;      // (1x1: memory-bound either way)
     return 0;
 }
 
@@ -548,7 +548,8 @@ bool iss_conv_f16_direct_covers(const ConvArgs &a)
     if (!a.wt_f16 || a.SH != 1 || a.SW != 1 || a.PT != 0 || a.PL != 0) return false;
     if (a.OH != a.H - a.KH + 1 || a.OW != a.W - a.KW + 1 || a.Kp != a.K) return false;
     const bool c_ok = a.C == 64 || a.C == 128 || a.C == 256 || (a.C == 32 && a.KH * a.KW == 1);
-    if (a.N % DBN != 0 || a.N > D_NMAX || !c_ok || a.K != a.KH * a.KW * a.C) return false;
+    const bool n_ok = (a.N % DBN == 0 && a.N <= D_NMAX) || (a.N == 32 && a.KH * a.KW == 1);     // N = 32: one n-tile, upper half masked
+    if (!n_ok || !c_ok || a.K != a.KH * a.KW * a.C) return false;
     if (a.flags & ISS_F_SIGMOID) return false;
     if (a.first && (a.C != HBK || a.pool_h > 0 || (a.flags & ISS_F_RESIDUAL))) return false;
     if (a.pool_h > 0 && (!a.in_packed || a.pool_h / 2 != a.H || a.pool_w / 2 != a.W)) return false;   // fused 2x2 / stride-2 'valid' pooling only
@@ -571,8 +572,8 @@ int iss_launch_conv_tc_f16d(ConvArgs &a, cudaStream_t st)
     d.total_pix = (int64_t)d.n_img * a.H * a.W;
     d.cb = direct_cb(a);
     d.c_real = a.C;
-    d.nt = a.N / DBN;
-    d.bn_img = iss_f16_bn_for(a.N);                                      // tiling of the weight image (iss_prepare_f16_weights)
+    d.nt = (a.N + DBN - 1) / DBN;
+    d.bn_img = iss_f16_bn_for(a.N == 32 ? 64 : a.N);                     // tiling of the weight image (iss_prepare_f16_weights)
     const char *nepi_env = getenv("ISS_B200_NEPI");                      // A/B runs: 4 or 8
     d.n_epi = nepi_env ? (atoi(nepi_env) == 8 ? 8 : 4) : ((a.flags & ISS_F_RESIDUAL) ? 8 : 4);
     const int64_t total_slots = ((int64_t)(d.n_img - 1) * a.H + a.OH - 1) * a.W + a.OW;

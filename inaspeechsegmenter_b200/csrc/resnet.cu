@@ -15,6 +15,7 @@
 // epilogue's per-channel affine, the residual add + ReLU are fused into the last 1x1
 // convolution of each block.
 #include <math.h>
+#include <stdlib.h>
 #include <vector>
 
 #include "conv_gemm.cuh"
@@ -148,7 +149,13 @@ int64_t max_act_per_window(const iss_resnet *net, int T, double *flops)
     return mx;
 }
 
-constexpr int RES_BATCH = 128;         // windows per sweep (layer4 then still has 128*8*18/128 = 144 M-tiles)
+// windows per sweep (128: layer4 then still has 128*8*18/128 = 144 M-tiles); ISS_B200_RES_BATCH: experiments, read once
+static int res_batch()
+{
+    static const int b = [] { const char *e = getenv("ISS_B200_RES_BATCH"); const int v = e ? atoi(e) : 0; return v >= 8 && v <= 1024 ? v : 128; }();
+    return b;
+}
+#define RES_BATCH res_batch()
 
 }  // namespace
 
@@ -184,7 +191,9 @@ extern "C" int iss_resnet_create(iss_ctx *ctx, const float *h_blob, int64_t blob
         if (c.cin % 32 != 0 || K % 32 != 0 || c.cout % 32 != 0) return ISS_OK;
         const int rc = iss_prepare_tc_weights(h_blob + c.w_off, K, c.cout, &c.d_wt, &c.Kp);
         // fp16-split image: 64-channel k-blocks; a 1x1 convolution over 32 channels is padded to one block (direct kernel only)
-        if (rc != ISS_OK || (c.cin % 64 != 0 && !(c.cin == 32 && c.kh * c.kw == 1)) || c.cout % 64 != 0) return rc;
+        // (and one with 32 outputs to one n-tile)
+        const bool one = c.kh * c.kw == 1;
+        if (rc != ISS_OK || (c.cin % 64 != 0 && !(c.cin == 32 && one)) || (c.cout % 64 != 0 && !(c.cout == 32 && one))) return rc;
         return iss_prepare_f16_weights(h_blob + c.w_off, K, c.cout, &c.d_wt_f16, &c.f16_inv_scale);
     };
     int prc = ISS_OK;
@@ -276,7 +285,7 @@ extern "C" int iss_resnet_embed(iss_ctx *ctx, iss_resnet *net, const float *d_fe
     // (a 32-channel 1x1 convolution has an image only the direct kernel reads: it counts when that kernel takes the layer)
     auto f16 = [&](const RConv &c) {
         if (!f16_mode || c.d_wt_f16 == nullptr) return false;
-        if (c.cin % 64 == 0) return true;
+        if (c.cin % 64 == 0 && c.cout % 64 == 0) return true;
         ConvArgs pr = {};
         pr.wt_f16 = c.d_wt_f16; pr.M = 1024; pr.N = c.cout; pr.K = c.kh * c.kw * c.cin; pr.Kp = c.Kp; pr.H = 32; pr.W = 32; pr.C = c.cin; pr.OH = 32; pr.OW = 32;
         pr.KH = c.kh; pr.KW = c.kw; pr.SH = c.stride; pr.SW = c.stride; pr.PT = c.pad; pr.PL = c.pad;

@@ -10,7 +10,8 @@ mkdir -p gpurun_out
   echo "== default (direct kernel)"; timeout 200 python tools/tc_check.py 3 10 2>&1 | grep -E "^mode|rror|timed out"
   echo "== ISS_B200_FUSE_POOL=0"; ISS_B200_FUSE_POOL=0 timeout 200 python tools/tc_check.py 3 10 2>&1 | grep -E "^mode|rror|timed out"
   echo "== resnet"; timeout 300 python tests/tools/resnet_check.py 2>&1 | grep -E "^mode|rror|Trace"
-  echo "== resnet ISS_B200_NEPI=4"; ISS_B200_NEPI=4 timeout 300 python tests/tools/resnet_check.py 2>&1 | grep -E "^mode 3|rror|Trace"
+  echo "== resnet ISS_B200_F16_BN=64"; ISS_B200_F16_BN=64 timeout 300 python tests/tools/resnet_check.py 2>&1 | grep -E "^mode 3|rror|Trace"
+  echo "== resnet ISS_B200_RES_BATCH=256"; ISS_B200_RES_BATCH=256 timeout 300 python tests/tools/resnet_check.py 2>&1 | grep -E "^mode 3|rror|Trace"
   echo "== resnet ISS_B200_F16_DIRECT=0"; ISS_B200_F16_DIRECT=0 timeout 300 python tests/tools/resnet_check.py 2>&1 | grep -E "^mode 3|rror|Trace"
 } > gpurun_out/${TAG}_ab.log 2>&1
 ( timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -40 ) > gpurun_out/${TAG}_pytest.log
