@@ -70,6 +70,7 @@ struct DirectArgs {
     int nt;                     // 64-channel n-tiles (N / 64)
     int bn_img;                 // n-tile width of the weight image (64 or 128, iss_f16_bn_for)
     int n_epi;                  // epilogue warps: 4 (one per TMEM lane quadrant, both sub-tiles) or 8 (one per quadrant and sub-tile)
+    int mma_order;              // 0: sub-tile major (default); 1: K-step major (experiment)
 };
 
 __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
@@ -85,6 +86,14 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, ui
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w)
 {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+// four epilogue constants (channels n .. n+3) as one LDS.128 broadcast.  The table is written once before the CTA-wide
+// barrier and never again, so the load is plain (not volatile) asm: the compiler may schedule it freely.
+// (Indexing the table through its generic pointer compiled to one 4-byte generic LD per constant -- 64-128 per 32
+// columns and warp, each a shared-memory wavefront competing with the tensor core's operand reads.)
+__device__ __forceinline__ void lds_f4(uint32_t addr, float (&v)[4])
+{
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr));
 }
 
 struct DSmem {                                           // everything behind the 1024-aligned operand buffers
@@ -103,7 +112,8 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d)
     unsigned char *slab = smem + DSB * D_B_STAGE;         // [NBUF buffers][channel block][hi plane | lo plane]
     const uint32_t slab_buf = 2u * (uint32_t)d.cb * plane;
     DSmem *sm = reinterpret_cast<DSmem *>(slab + (size_t)NBUF * slab_buf);
-    float *cst = reinterpret_cast<float *>(sm + 1);       // k1 | k0 | es2 | et2, N floats each (y = acc * k1 + k0, ReLU, y * es2 + et2)
+    // k1 | k0 | es2 | et2, N floats each (y = acc * k1 + k0, ReLU, y * es2 + et2); 16-byte aligned for the epilogue's LDS.128
+    float *cst = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(sm + 1) + 15) & ~(uintptr_t)15);
     const int n_fill_warps = D_WARPS - 2 - d.n_epi, first_fill = 2 + d.n_epi, nfill = 32 * n_fill_warps;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -164,15 +174,30 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d)
                     const uint64_t db = make_sw128_desc(b_u32 + sl * D_B_STAGE);
                     const uint32_t tap = slab_b + (uint32_t)cb * 2u * plane + (uint32_t)(kh * a.W + kw) * 128u;
                     if (elect_one()) {
+                        if (d.mma_order == 0) {
 #pragma unroll
-                        for (int t = 0; t < DT; ++t) {
-                            const uint32_t arow = tap + (uint32_t)t * (128u * 128u);
-                            const uint64_t dah = make_sw128_desc(arow), dal = make_sw128_desc(arow + plane);   // base-offset field stays 0
-                            const uint32_t dm = tb + abuf * 256u + (uint32_t)t * 128u;
+                            for (int t = 0; t < DT; ++t) {
+                                const uint32_t arow = tap + (uint32_t)t * (128u * 128u);
+                                const uint64_t dah = make_sw128_desc(arow), dal = make_sw128_desc(arow + plane);   // base-offset field stays 0
+                                const uint32_t dm = tb + abuf * 256u + (uint32_t)t * 128u;
+#pragma unroll
+                                for (int kk = 0; kk < HBK / 16; ++kk) {
+                                    umma_f16_ss(dm, dah + 2 * kk, db + 2 * kk, idesc2, (kb > 0 || kk > 0) ? 1u : 0u);     // Ah.[Bh | Bl]
+                                    umma_f16_ss(dm + DBN, dal + 2 * kk, db + 2 * kk, idesc, 1u);                          // Al.Bh
+                                }
+                            }
+                        } else {
+                            // experiment (ISS_B200_MMA_ORDER=1): K-step major, the two sub-tiles back to back on the same weight columns
+                            const uint64_t dah0 = make_sw128_desc(tap), dal0 = make_sw128_desc(tap + plane);
+                            const uint64_t dah1 = make_sw128_desc(tap + 128u * 128u), dal1 = make_sw128_desc(tap + 128u * 128u + plane);
+                            const uint32_t dm0 = tb + abuf * 256u, dm1 = dm0 + 128u;
 #pragma unroll
                             for (int kk = 0; kk < HBK / 16; ++kk) {
-                                umma_f16_ss(dm, dah + 2 * kk, db + 2 * kk, idesc2, (kb > 0 || kk > 0) ? 1u : 0u);     // Ah.[Bh | Bl]
-                                umma_f16_ss(dm + DBN, dal + 2 * kk, db + 2 * kk, idesc, 1u);                          // Al.Bh
+                                const uint32_t acc = (kb > 0 || kk > 0) ? 1u : 0u;
+                                umma_f16_ss(dm0, dah0 + 2 * kk, db + 2 * kk, idesc2, acc);
+                                umma_f16_ss(dm1, dah1 + 2 * kk, db + 2 * kk, idesc2, acc);
+                                umma_f16_ss(dm0 + DBN, dal0 + 2 * kk, db + 2 * kk, idesc, 1u);
+                                umma_f16_ss(dm1 + DBN, dal1 + 2 * kk, db + 2 * kk, idesc, 1u);
                             }
                         }
                         umma_commit(&sm->b_empty[sl]);
@@ -223,6 +248,7 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d)
         // 8 epilogue warps: warps 2-5 take sub-tile 0, warps 6-9 sub-tile 1 (twice the loads / stores in flight: the residual
         // layers are bound by memory latency x bytes in flight, not by instructions)
         const int t_first = d.n_epi == 8 ? ((warp - 2) >> 2) : 0, t_last = d.n_epi == 8 ? t_first + 1 : DT;
+        const uint32_t cst_u32 = smem_u32(cst), cst_arr = 4u * (uint32_t)a.N;         // byte address of the table, bytes per array
         uint32_t p = 0;
         for (int tile = blockIdx.x; tile < d.n_tiles; tile += gridDim.x) {
             for (int nt = 0; nt < d.nt; ++nt, ++p) {
@@ -270,13 +296,19 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d)
                                 for (int j = 0; j < 4; ++j) {
                                     float y[8];
 #pragma unroll
-                                    for (int q = 0; q < 8; ++q) {
-                                        const int n = nb + c + 8 * j + q;
-                                        float v = fmaf(__uint_as_float(acc[8 * j + q]), cst[n], cst[a.N + n]);
-                                        if (resid) v += a.residual_packed ? iss_unpack_split(rw[j].v[q]) : __uint_as_float(rw[j].v[q]);
-                                        if (relu) v = fmaxf(v, 0.f);
-                                        if (post) v = fmaf(v, cst[2 * a.N + n], cst[3 * a.N + n]);
-                                        y[q] = v;
+                                    for (int h = 0; h < 2; ++h) {
+                                        float k1[4], k0[4], s2[4], t2[4];
+                                        const uint32_t cj = cst_u32 + 4u * (uint32_t)(nb + c + 8 * j + 4 * h);   // constants of channels nb + c + 8j + 4h ..
+                                        lds_f4(cj, k1); lds_f4(cj + cst_arr, k0);
+                                        if (post) { lds_f4(cj + 2u * cst_arr, s2); lds_f4(cj + 3u * cst_arr, t2); }
+#pragma unroll
+                                        for (int q = 0; q < 4; ++q) {
+                                            float v = fmaf(__uint_as_float(acc[8 * j + 4 * h + q]), k1[q], k0[q]);
+                                            if (resid) v += a.residual_packed ? iss_unpack_split(rw[j].v[4 * h + q]) : __uint_as_float(rw[j].v[4 * h + q]);
+                                            if (relu) v = fmaxf(v, 0.f);
+                                            if (post) v = fmaf(v, s2[q], t2[q]);
+                                            y[4 * h + q] = v;
+                                        }
                                     }
                                     u32x8 w;
                                     if (a.out_packed) {
@@ -511,16 +543,17 @@ int direct_cb(const ConvArgs &a) { return (a.C + HBK - 1) / HBK; }
 
 size_t direct_smem(const ConvArgs &a, int nbuf)
 {
-    return (size_t)DSB * D_B_STAGE + (size_t)nbuf * 2 * direct_cb(a) * direct_npix(a) * 128 + sizeof(DSmem) + 1024 + (size_t)4 * a.N * sizeof(float);
+    return (size_t)DSB * D_B_STAGE + (size_t)nbuf * 2 * direct_cb(a) * direct_npix(a) * 128 + sizeof(DSmem) + 1024 + 16 + (size_t)4 * a.N * sizeof(float);
 }
 
 // slab buffers: two when they fit (fill of tile i+1 under the MMAs of tile i); one is accepted only when a tile has >= 4
 // n-tile passes to amortise the exposed fill (on the 3x3 128 -> 128 layer, 2 passes, one buffer measured slower than
-// the TMEM-operand slab kernel: 286 vs 208 us)
+// the TMEM-operand slab kernel: 286 vs 208 us; 1x1 layers with C = 128 and N = 32 / 64 measured 273 / 292 us with one
+// buffer against 230 / 262 us on the gather kernels -- gpurun_out r02j -- so they stay there)
 int direct_nbuf(const ConvArgs &a)
 {
     if (direct_smem(a, 2) <= (size_t)D_SMEM_MAX) return 2;
-    if (direct_smem(a, 1) <= (size_t)D_SMEM_MAX && (a.N / DBN >= 4 || a.KH * a.KW == 1)) return 1;      // (1x1: memory-bound either way)
+    if (direct_smem(a, 1) <= (size_t)D_SMEM_MAX && a.N / DBN >= 4) return 1;
     return 0;
 }
 
@@ -576,6 +609,8 @@ int iss_launch_conv_tc_f16d(ConvArgs &a, cudaStream_t st)
     d.bn_img = iss_f16_bn_for(a.N == 32 ? 64 : a.N);                     // tiling of the weight image (iss_prepare_f16_weights)
     const char *nepi_env = getenv("ISS_B200_NEPI");                      // A/B runs: 4 or 8
     d.n_epi = nepi_env ? (atoi(nepi_env) == 8 ? 8 : 4) : ((a.flags & ISS_F_RESIDUAL) ? 8 : 4);
+    const char *ord_env = getenv("ISS_B200_MMA_ORDER");
+    d.mma_order = ord_env && ord_env[0] == '1' ? 1 : 0;
     const int64_t total_slots = ((int64_t)(d.n_img - 1) * a.H + a.OH - 1) * a.W + a.OW;
     d.n_tiles = (int)((total_slots + DT * 128 - 1) / (DT * 128));
     int dev = 0, sms = 0;
