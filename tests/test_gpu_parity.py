@@ -419,6 +419,27 @@ def test_cli_with_hdf5_models(rt, synth_models, media, tmp_path, monkeypatch):
     assert got[0] == ref[0] and [l for l in got if l.startswith('noEnergy')] == [l for l in ref if l.startswith('noEnergy')]
 
 
+def test_cli_devices_spawns_one_worker_per_device(rt, synth_models, media, tmp_path, monkeypatch):
+    """`--devices a,b` (cli.py: files dealt round-robin to one spawned process per device -- the role of the reference's
+    Pyro farm, scripts/ina_speech_segmenter_pyro_client.py:64-74, on one host): the outputs are byte-identical to the
+    single-process run.  On a one-GPU box both workers share device 0."""
+    import torch
+    from inaspeechsegmenter_b200 import cli, keras_hdf5, models as M
+    mdir = tmp_path / 'models'
+    mdir.mkdir()
+    keras_hdf5.write_keras_hdf5(str(mdir / 'keras_speech_music_noise_cnn.hdf5'), *synth_models['smn'])
+    keras_hdf5.write_keras_hdf5(str(mdir / 'keras_male_female_cnn.hdf5'), *synth_models['gender'])
+    monkeypatch.setenv(M.MODEL_DIR_ENV, str(mdir))
+    files = [os.path.join(media, f) for f in ('silence2sec.wav', 'musanmix.wav', 'lamartine.wav')]
+    one, two = tmp_path / 'one', tmp_path / 'two'
+    one.mkdir(); two.mkdir()
+    cli.main(['-i'] + files + ['-o', str(one), '-b', 'None'])
+    devs = '0,1' if torch.cuda.device_count() > 1 else '0,0'
+    cli.main(['-i'] + files + ['-o', str(two), '-b', 'None', '--devices', devs])
+    for f in ('silence2sec.csv', 'musanmix.csv', 'lamartine.csv'):
+        assert (two / f).read_bytes() == (one / f).read_bytes(), f
+
+
 def _alt_keras_cnn(nmel, n_classes, seed):
     """A second architecture exercising the rest of the layer interpreter: 'same' padding, strides,
     'same' max-pooling with odd sizes, activation fused in the Conv2D config, Dense -> ReLU -> BatchNorm

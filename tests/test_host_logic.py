@@ -187,3 +187,41 @@ def test_bench_reference_arm_contract():
         assert k in d, k
     assert d['impl'] == 'reference' and d['value'] > 0 and d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
     assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['value'] == d['value']
+
+
+def test_ffmpeg_branch_with_stand_in_binary(media, tmp_path):
+    """The ffmpeg subprocess branch of media2sig16kmono (reference io.py:60-79): no ffmpeg exists in any of the
+    boxes, so a stand-in executable checks the argv the reference builds (-i <media> -f wav -acodec pcm_s16le
+    -ar 16000 -ac 1 [-ss a] [-to b] pipe:1), cuts the 16 kHz WAV like ffmpeg would and pipes it with the
+    0xFFFFFFFF chunk sizes ffmpeg writes on a pipe; a failing binary must surface its stderr as the exception."""
+    import stat
+    import sys
+    fake = tmp_path / 'ffmpeg'
+    fake.write_text('''#!%s
+import struct, sys
+a = sys.argv[1:]
+assert a[0] == '-i' and a[2:10] == ['-f', 'wav', '-acodec', 'pcm_s16le', '-ar', '16000', '-ac', '1'] and a[-1] == 'pipe:1', a
+if a[1].endswith('broken.wav'):
+    sys.stderr.write('broken.wav: Invalid data found when processing input')
+    sys.exit(1)
+rest = a[10:-1]
+ss = float(rest[rest.index('-ss') + 1]) if '-ss' in rest else 0.0
+to = float(rest[rest.index('-to') + 1]) if '-to' in rest else None
+raw = open(a[1], 'rb').read()
+p = raw.index(b'data') + 8
+pcm = raw[p:]
+pcm = pcm[2 * int(round(ss * 16000)):(2 * int(round(to * 16000)) if to is not None else None)]
+hdr = b'RIFF' + struct.pack('<I', 0xFFFFFFFF) + b'WAVEfmt ' + struct.pack('<IHHIIHH', 16, 1, 1, 16000, 32000, 2, 16)
+sys.stdout.buffer.write(hdr + b'data' + struct.pack('<I', 0xFFFFFFFF) + pcm)
+''' % sys.executable)
+    fake.chmod(fake.stat().st_mode | stat.S_IXUSR)
+    wav = os.path.join(media, 'musanmix.wav')
+    direct = iss_io.media2sig16kmono(wav, ffmpeg=None, dtype='float32')
+    piped = iss_io.media2sig16kmono(wav, ffmpeg=str(fake), dtype='float32')
+    assert piped.dtype == np.float32 and np.array_equal(piped, direct)
+    cut = iss_io.media2sig16kmono(wav, start_sec=1.5, stop_sec=4.25, ffmpeg=str(fake), dtype='float64')
+    assert cut.dtype == np.float64 and np.array_equal(cut, direct[24000:68000].astype(np.float64))
+    raw16 = iss_io.media2sig16kmono(wav, stop_sec=2.0, ffmpeg=str(fake), return_int16=True)
+    assert raw16.dtype == np.int16 and len(raw16) == 32000
+    with pytest.raises(Exception, match='Invalid data found'):
+        iss_io.media2sig16kmono(str(tmp_path / 'broken.wav'), ffmpeg=str(fake))
