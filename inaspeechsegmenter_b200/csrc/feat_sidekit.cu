@@ -14,6 +14,11 @@
 // transpose through shared memory + two rounds of shuffles: fft256r.cuh) followed
 // by the even/odd split.  (Round 1 used a 4-pass radix-4 Stockham FFT through shared
 // memory; with float64 data that was shared-memory bound: 33 % conflict wavefronts.)
+// Round 2, second pass (the kernel was shared-memory bound at 580 wavefronts per frame): the even/odd split takes
+// Z[256 - k] from its partner lane with register shuffles instead of a round trip of the spectrum through shared
+// memory (partner lane / register algebra: tests/test_k1_split_model.py), the split twiddles are staged in lane order
+// (conflict-free), and the 24 mel sums run as <= 32 balanced tasks (<= 24 bins each; a filter is up to three tasks)
+// on all lanes instead of 24 lanes walking up to 48 bins.
 // T = float: fast path; T = double: window/FFT/power in fp64 then rounded to f32,
 // which is the reference's own precision recipe (sidekit_mfcc.py:231-233).
 #include <math.h>
@@ -31,7 +36,7 @@ constexpr int FR = 48;                               // frames per CTA tile (int
 constexpr int NWARP = 8;
 constexpr int NTHREAD = NWARP * 32;
 constexpr int TILE_SAMPLES = (FR - 1) * ISS_HOP + ISS_WIN;   // 7920
-constexpr int ZPAD = 272;                            // 257 + skew, padded
+constexpr int ZPAD = 296;                            // power spectrum P[k] at k + 8 (k >> 6): 257 + 32, padded
 
 
 template <typename T> struct Tab;
@@ -55,13 +60,17 @@ struct Smem {
     T win[ISS_WIN];
     Cplx<T> twA[7 * 32];                    // W256^(lane * k1), k1 = 1..7 (fft256r.cuh)
     Cplx<T> twB[7 * 4];                     // W32^(r * k2a),   k2a = 1..7
-    T tw512[2 * 257 + 2];
+    Cplx<T> twS[8 * 32];                    // W512^k of the bin lane l holds in register a, at [a * 32 + l] (split stage)
     float fbw[ISS_FB_MAXNNZ];
-    int fb_lo[ISS_NMEL], fb_cnt[ISS_NMEL], fb_off[ISS_NMEL];
-    Cplx<T> buf[NWARP][FFT_BUF];            // per-warp transpose rows, then the spectrum Z[k] at k + 2 (k >> 6)
+    int task_lo[32], task_cnt[32], task_off[32];      // mel tasks: bins [lo, lo + cnt) with weights fbw[off ..]
+    int filt_first[ISS_NMEL], filt_n[ISS_NMEL];      // filter m = tasks [first, first + n)
+    Cplx<T> buf[NWARP][FFT_BUF];            // per-warp transpose rows of the FFT
     float pw[NWARP][ZPAD];
+    T part[NWARP][32];                      // per-task partial mel sums
     double red[NWARP][2];
 };
+
+__device__ __forceinline__ int bitrev2(int r) { return ((r & 1) << 1) | ((r >> 1) & 1); }
 
 template <typename T, int PCM>
 __global__ void __launch_bounds__(NTHREAD, 3)
@@ -87,9 +96,13 @@ sidekit_features_kernel(const void *__restrict__ pcm, int64_t n_samples, int64_t
         const int k = tid / 4 + 1, r = tid % 4;
         S.twB[tid].x = Tab<T>::tw256(tabs)[2 * (8 * r * k)]; S.twB[tid].y = Tab<T>::tw256(tabs)[2 * (8 * r * k) + 1];
     }
-    for (int i = tid; i < 2 * 257; i += NTHREAD) S.tw512[i] = Tab<T>::tw512(tabs)[i];
+    for (int i = tid; i < 8 * 32; i += NTHREAD) {                // lane l, register a holds bin (l >> 2) + 8 a + 64 bitrev2(l & 3)
+        const int a = i >> 5, l = i & 31, k = (l >> 2) + 8 * a + 64 * bitrev2(l & 3);
+        S.twS[i].x = Tab<T>::tw512(tabs)[2 * k]; S.twS[i].y = Tab<T>::tw512(tabs)[2 * k + 1];
+    }
     for (int i = tid; i < tabs->nnz; i += NTHREAD) S.fbw[i] = tabs->w[i];
-    if (tid < ISS_NMEL) { S.fb_lo[tid] = tabs->lo[tid]; S.fb_cnt[tid] = tabs->cnt[tid]; S.fb_off[tid] = tabs->off[tid]; }
+    if (tid < 32) { S.task_lo[tid] = tabs->task_lo[tid]; S.task_cnt[tid] = tabs->task_cnt[tid]; S.task_off[tid] = tabs->task_off[tid]; }
+    if (tid < ISS_NMEL) { S.filt_first[tid] = tabs->filt_first[tid]; S.filt_n[tid] = tabs->filt_n[tid]; }
 
     if (PCM == ISS_PCM_S16) {
         const int16_t *p = reinterpret_cast<const int16_t *>(pcm) + s0;
@@ -121,12 +134,31 @@ sidekit_features_kernel(const void *__restrict__ pcm, int64_t n_samples, int64_t
     Cplx<T> *buf = S.buf[warp];
     float *pw = S.pw[warp];
     double acc_sum = 0.0, acc_cnt = 0.0;
-    const int zk1 = lane >> 2, zk2b = ((lane & 1) << 1) | ((lane >> 1) & 1);   // where this lane's FFT outputs belong
+    T *part = S.part[warp];
+    // After the FFT this lane holds Z[k], k = zk1 + 8 a + 64 zk2b, in register a.  The split needs Z[256 - k]: it sits in
+    // lane (8 - zk1) | (3 - r) at register 7 - a; for zk1 = 0 in lane 3 - r at register 8 - a, and for zk1 = 0, a = 0
+    // (k = 0, 128, 64, 192) in lane {0, 1, 3, 2}[r].  Partners are always of the same class (zk1 = 0 or not), so the
+    // SOURCE lane selects which register it sends.
+    const int zk1 = lane >> 2, zr4 = lane & 3, zk2b = bitrev2(zr4);
+    const bool cls0 = zk1 == 0;
+    const int src_gen = cls0 ? (3 - zr4) : ((((8 - zk1) & 7) << 2) | (3 - zr4));
+    const int src_a0 = cls0 ? (zr4 ^ (zr4 >> 1)) : src_gen;                      // {0, 1, 3, 2}[r]
+    const int kbase = zk1 + 64 * zk2b;
 
     for (int fl = warp; fl < nfr; fl += NWARP) {
         const auto *xs = S.samples + fl * ISS_HOP;
         auto x = [&](int n) -> float {
             return (PCM == ISS_PCM_S16) ? (float)xs[n] * (1.0f / 32768.0f) : (float)xs[n];
+        };
+        // samples n, n + 1 (n even, the tile offset fl * 160 is even) in one load
+        auto x2 = [&](int n, float &xa, float &xb) {
+            if (PCM == ISS_PCM_S16) {
+                const short2 v = *reinterpret_cast<const short2 *>(xs + n);
+                xa = (float)v.x * (1.0f / 32768.0f); xb = (float)v.y * (1.0f / 32768.0f);
+            } else {
+                const float2 v = *reinterpret_cast<const float2 *>(xs + n);
+                xa = v.x; xb = v.y;
+            }
         };
         // ---- pre-emphasis (f32, numpy op order: x - (x_prev * 0.97f)), energy, window; the 512-point real
         //      frame is packed as z[m] = v[2m] + i v[2m+1] and lane l keeps z[32 n1 + l], n1 = 0..7, in registers ----
@@ -137,7 +169,8 @@ sidekit_features_kernel(const void *__restrict__ pcm, int64_t n_samples, int64_t
             const int n = 64 * n1 + 2 * lane;            // even sample of z[32 n1 + lane]; ISS_WIN is even
             T v0 = (T)0, v1 = (T)0;
             if (n < ISS_WIN) {
-                const float xa = x(n), xb = x(n + 1);
+                float xa, xb;
+                x2(n, xa, xb);
                 const float xp = (n == 0) ? xa : x(n - 1);
                 const float y0 = __fsub_rn(xa, __fmul_rn(xp, 0.97f));
                 const float y1 = __fsub_rn(xb, __fmul_rn(xa, 0.97f));
@@ -153,43 +186,46 @@ sidekit_features_kernel(const void *__restrict__ pcm, int64_t n_samples, int64_t
 
         warp_fft256_reg<T>(zr, zi, buf, S.twA, S.twB, lane);
 
-        // ---- spectrum to shared memory (Z[k] at k + 2 (k >> 6): conflict-free 16-byte stores), then the split
-        //      X[k] = E[k] + W512^k O[k], power -> f32 ----
+        // ---- even/odd split X[k] = E[k] + W512^k O[k] with Z[256 - k] from the partner lane (shuffles), power -> f32 at
+        //      pw[k + 8 (k >> 6)] (conflict-free: the 32 lanes' bins of one register cover all banks) ----
 #pragma unroll
-        for (int k2a = 0; k2a < 8; ++k2a) {
-            Cplx<T> v; v.x = zr[k2a]; v.y = zi[k2a];
-            buf[zk1 + 8 * k2a + 64 * zk2b + 2 * zk2b] = v;
-        }
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 9; ++i) {
-            const int k = lane + 32 * i;
-            if (k <= 256) {
-                const int ka = k & 255, kb = (256 - k) & 255;
-                const Cplx<T> za = buf[ka + 2 * (ka >> 6)], zb = buf[kb + 2 * (kb >> 6)];
-                const T zr_ = za.x, zi_ = za.y;
-                const T cr = zb.x, ci = -zb.y;                      // conj(Z[256-k])
-                const T er = (T)0.5 * (zr_ + cr), ei = (T)0.5 * (zi_ + ci);
-                const T dr = (T)0.5 * (zr_ - cr), di = (T)0.5 * (zi_ - ci);
-                const T orr = di, oi = -dr;                          // O = -i * (Z - conj)/2
-                const T c = S.tw512[2 * k], sn = S.tw512[2 * k + 1];
-                const T xr = er + (orr * c - oi * sn);
-                const T xi = ei + (orr * sn + oi * c);
-                pw[k + (k >> 5)] = (float)(xr * xr + xi * xi);
+        for (int a = 0; a < 8; ++a) {
+            const T sr = cls0 ? zr[(8 - a) & 7] : zr[7 - a], si = cls0 ? zi[(8 - a) & 7] : zi[7 - a];
+            const int src = (a == 0) ? src_a0 : src_gen;
+            const T cr = __shfl_sync(0xffffffffu, sr, src), ci = -__shfl_sync(0xffffffffu, si, src);      // conj(Z[256-k])
+            const T zr_ = zr[a], zi_ = zi[a];
+            const T er = (T)0.5 * (zr_ + cr), ei = (T)0.5 * (zi_ + ci);
+            const T dr = (T)0.5 * (zr_ - cr), di = (T)0.5 * (zi_ - ci);
+            const T orr = di, oi = -dr;                              // O = -i * (Z - conj)/2
+            const Cplx<T> w = S.twS[a * 32 + lane];
+            const T xr = er + (orr * w.x - oi * w.y);
+            const T xi = ei + (orr * w.y + oi * w.x);
+            const int k = kbase + 8 * a;
+            pw[k + 8 * (k >> 6)] = (float)(xr * xr + xi * xi);
+            if (a == 0 && lane == 0) {                               // k = 0 also yields the Nyquist bin: X[256] = Re Z[0] - Im Z[0]
+                const T xn = zr_ - zi_;
+                pw[256 + 8 * 4] = (float)(xn * xn);
             }
         }
         __syncwarp();
 
-        // ---- mel filterbank (sparse triangles) + log ----
+        // ---- mel filterbank (sparse triangles) as balanced tasks on all lanes, then <= 3 partials per filter + log ----
         const int64_t f = f0 + fl;
-        if (lane < ISS_NMEL) {
-            const int lo = S.fb_lo[lane], cnt = S.fb_cnt[lane];
-            const float *w = S.fbw + S.fb_off[lane];
+        {
+            const int lo = S.task_lo[lane], cnt = S.task_cnt[lane];
+            const float *w = S.fbw + S.task_off[lane];
             T acc = (T)0;
             for (int b = 0; b < cnt; ++b) {
                 const int k = lo + b;
-                acc += (T)pw[k + (k >> 5)] * (T)w[b];
+                acc += (T)pw[k + 8 * (k >> 6)] * (T)w[b];
             }
+            part[lane] = acc;
+        }
+        __syncwarp();
+        if (lane < ISS_NMEL) {
+            const int t0 = S.filt_first[lane], tn = S.filt_n[lane];
+            T acc = (T)0;
+            for (int t = 0; t < tn; ++t) acc += part[t0 + t];
             mspec[f * ISS_NMEL + lane] = Tab<T>::log_((T)(float)acc);
         }
         const float le = Tab<T>::log_((T)(float)e);
@@ -309,6 +345,27 @@ extern "C" int iss_sidekit_upload_tables(iss_ctx *ctx, const float *h_fbank, con
         for (int b = 0; b < t->cnt[m]; ++b) t->w[nnz++] = h_fbank[m * ISS_NBIN + lo + b];
     }
     t->nnz = nnz;
+    {   // balanced mel tasks: the smallest cap (bins per task) for which all filters fit 32 tasks; a filter's bins are
+        // dealt to its tasks as evenly as possible
+        int cap = 1;
+        for (;; ++cap) {
+            int n = 0;
+            for (int m = 0; m < ISS_NMEL; ++m) n += (t->cnt[m] + cap - 1) / cap;
+            if (n <= 32) break;
+        }
+        int nt = 0;
+        for (int m = 0; m < ISS_NMEL; ++m) {
+            const int parts = (t->cnt[m] + cap - 1) / cap;
+            t->filt_first[m] = nt; t->filt_n[m] = parts;
+            int done = 0;
+            for (int q = 0; q < parts; ++q) {
+                const int len = (t->cnt[m] - done + (parts - q) - 1) / (parts - q);
+                t->task_lo[nt] = t->lo[m] + done; t->task_cnt[nt] = len; t->task_off[nt] = t->off[m] + done;
+                done += len; ++nt;
+            }
+        }
+        for (; nt < 32; ++nt) { t->task_lo[nt] = 0; t->task_cnt[nt] = 0; t->task_off[nt] = 0; }
+    }
     const double PI = 3.14159265358979323846;
     for (int i = 0; i < ISS_WIN; ++i) { t->win64[i] = h_window[i]; t->win32[i] = (float)h_window[i]; }
     for (int m = 0; m < 256; ++m) {

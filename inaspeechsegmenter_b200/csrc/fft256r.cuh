@@ -47,7 +47,7 @@ __device__ __forceinline__ void dft8(T (&re)[8], T (&im)[8])
 template <typename T> struct Cplx { T x, y; };      // 16-byte (double) / 8-byte (float) shared-memory element
 
 constexpr int FFT_ROW = 36;                         // complex elements per transpose row (32 + 4: rows 64 bytes apart mod 128)
-constexpr int FFT_BUF = 8 * FFT_ROW;                // 288 complex per warp; also holds Z[k] at k + 2 (k >> 6) afterwards
+constexpr int FFT_BUF = 8 * FFT_ROW;                // 288 complex per warp
 
 // twA: [7][32] W256^(lane * k1), k1 = 1..7;  twB: [7][4] W32^(r * k2a), k2a = 1..7 (both (cos, -sin) pairs)
 // in: zr/zi[n1] = z[32 n1 + lane].  out: zr/zi[k2a] = Z[k1 + 8 (k2a + 8 k2b)], k1 = lane >> 2, k2b = bitrev2(lane & 3).

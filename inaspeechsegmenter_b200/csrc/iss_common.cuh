@@ -41,6 +41,10 @@ struct SidekitTables {
     int off[ISS_NMEL];
     int nnz;
     float w[ISS_FB_MAXNNZ];
+    // the same sums as <= 32 balanced tasks (one per lane): task t covers bins [task_lo, task_lo + task_cnt) with weights
+    // w[task_off ..]; filter m is the sum of tasks [filt_first[m], filt_first[m] + filt_n[m]) (feat_sidekit.cu)
+    int task_lo[32], task_cnt[32], task_off[32];
+    int filt_first[ISS_NMEL], filt_n[ISS_NMEL];
     float win32[ISS_WIN];
     double win64[ISS_WIN];
     float tw256_32[2 * 256];   // W_256^m  (cos, -sin) interleaved
