@@ -70,7 +70,6 @@ struct DirectArgs {
     int nt;                     // 64-channel n-tiles (N / 64)
     int bn_img;                 // n-tile width of the weight image (64 or 128, iss_f16_bn_for)
     int n_epi;                  // epilogue warps: 4 (one per TMEM lane quadrant, both sub-tiles) or 8 (one per quadrant and sub-tile)
-    int mma_order;              // 0: sub-tile major (default); 1: K-step major (experiment)
 };
 
 __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
@@ -174,30 +173,16 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d)
                     const uint64_t db = make_sw128_desc(b_u32 + sl * D_B_STAGE);
                     const uint32_t tap = slab_b + (uint32_t)cb * 2u * plane + (uint32_t)(kh * a.W + kw) * 128u;
                     if (elect_one()) {
-                        if (d.mma_order == 0) {
 #pragma unroll
-                            for (int t = 0; t < DT; ++t) {
-                                const uint32_t arow = tap + (uint32_t)t * (128u * 128u);
-                                const uint64_t dah = make_sw128_desc(arow), dal = make_sw128_desc(arow + plane);   // base-offset field stays 0
-                                const uint32_t dm = tb + abuf * 256u + (uint32_t)t * 128u;
-#pragma unroll
-                                for (int kk = 0; kk < HBK / 16; ++kk) {
-                                    umma_f16_ss(dm, dah + 2 * kk, db + 2 * kk, idesc2, (kb > 0 || kk > 0) ? 1u : 0u);     // Ah.[Bh | Bl]
-                                    umma_f16_ss(dm + DBN, dal + 2 * kk, db + 2 * kk, idesc, 1u);                          // Al.Bh
-                                }
-                            }
-                        } else {
-                            // experiment (ISS_B200_MMA_ORDER=1): K-step major, the two sub-tiles back to back on the same weight columns
-                            const uint64_t dah0 = make_sw128_desc(tap), dal0 = make_sw128_desc(tap + plane);
-                            const uint64_t dah1 = make_sw128_desc(tap + 128u * 128u), dal1 = make_sw128_desc(tap + 128u * 128u + plane);
-                            const uint32_t dm0 = tb + abuf * 256u, dm1 = dm0 + 128u;
+                        for (int t = 0; t < DT; ++t) {
+                            const uint32_t arow = tap + (uint32_t)t * (128u * 128u);
+                            const uint64_t dah = make_sw128_desc(arow), dal = make_sw128_desc(arow + plane);   // base-offset field stays 0
+                            const uint32_t dm = tb + abuf * 256u + (uint32_t)t * 128u;
+                            // (K-step-major order -- both sub-tiles back to back on the same weight columns -- measured 0.5 % slower: r02k)
 #pragma unroll
                             for (int kk = 0; kk < HBK / 16; ++kk) {
-                                const uint32_t acc = (kb > 0 || kk > 0) ? 1u : 0u;
-                                umma_f16_ss(dm0, dah0 + 2 * kk, db + 2 * kk, idesc2, acc);
-                                umma_f16_ss(dm1, dah1 + 2 * kk, db + 2 * kk, idesc2, acc);
-                                umma_f16_ss(dm0 + DBN, dal0 + 2 * kk, db + 2 * kk, idesc, 1u);
-                                umma_f16_ss(dm1 + DBN, dal1 + 2 * kk, db + 2 * kk, idesc, 1u);
+                                umma_f16_ss(dm, dah + 2 * kk, db + 2 * kk, idesc2, (kb > 0 || kk > 0) ? 1u : 0u);     // Ah.[Bh | Bl]
+                                umma_f16_ss(dm + DBN, dal + 2 * kk, db + 2 * kk, idesc, 1u);                          // Al.Bh
                             }
                         }
                         umma_commit(&sm->b_empty[sl]);
@@ -249,34 +234,60 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d)
         // layers are bound by memory latency x bytes in flight, not by instructions)
         const int t_first = d.n_epi == 8 ? ((warp - 2) >> 2) : 0, t_last = d.n_epi == 8 ? t_first + 1 : DT;
         const uint32_t cst_u32 = smem_u32(cst), cst_arr = 4u * (uint32_t)a.N;         // byte address of the table, bytes per array
+        // 8 channels (n0 ..) of this lane's row: bias/BN affine (+ residual words rw) / ReLU / second affine -> 32 bytes to HBM
+        auto finish8 = [&](const uint32_t *acc, const u32x8 &rw, int n0, float *dst) {
+            float y[8];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float k1[4], k0[4], s2[4], t2[4];
+                const uint32_t cj = cst_u32 + 4u * (uint32_t)(n0 + 4 * h);
+                lds_f4(cj, k1); lds_f4(cj + cst_arr, k0);
+                if (post) { lds_f4(cj + 2u * cst_arr, s2); lds_f4(cj + 3u * cst_arr, t2); }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float v = fmaf(__uint_as_float(acc[4 * h + q]), k1[q], k0[q]);
+                    if (resid) v += a.residual_packed ? iss_unpack_split(rw.v[4 * h + q]) : __uint_as_float(rw.v[4 * h + q]);
+                    if (relu) v = fmaxf(v, 0.f);
+                    if (post) v = fmaf(v, s2[q], t2[q]);
+                    y[4 * h + q] = v;
+                }
+            }
+            u32x8 w;
+            if (a.out_packed) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) iss_pack_split2(y[2 * q], y[2 * q + 1], w.v[2 * q], w.v[2 * q + 1]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) w.v[q] = __float_as_uint(y[q]);
+            }
+            stg256(dst, w);
+        };
         uint32_t p = 0;
         for (int tile = blockIdx.x; tile < d.n_tiles; tile += gridDim.x) {
             for (int nt = 0; nt < d.nt; ++nt, ++p) {
                 const uint32_t abuf = p & 1u, ause = (p >> 1) & 1u;
-                if (lane == 0) mbar_wait(&sm->acc_full[abuf], ause, 5);
-                __syncwarp();
-                tc_fence_after();
                 const int nb = nt * DBN;
-#pragma unroll 1
-                for (int t = t_first; t < t_last; ++t) {
-                    const uint32_t slot = (uint32_t)tile * (DT * 128u) + (uint32_t)t * 128u + (uint32_t)(quad * 32 + lane);
+                const int ncol = a.N - nb < DBN ? a.N - nb : DBN;    // (N = 32: only the first 32 columns exist)
+                // this lane's row of sub-tile t: slot -> (image, oh, ow), validity, offset of its channels nb ..
+                uint32_t slot; bool valid; int64_t orow;
+                auto geometry = [&](int t) {
+                    slot = (uint32_t)tile * (DT * 128u) + (uint32_t)t * 128u + (uint32_t)(quad * 32 + lane);
                     const uint32_t img = slot / HW, rem = slot - img * HW;
                     const uint32_t oh = rem / (uint32_t)a.W, ow = rem - oh * (uint32_t)a.W;
-                    const bool valid = img < (uint32_t)d.n_img && oh < (uint32_t)a.OH && ow < (uint32_t)a.OW;
-                    const int64_t orow = (((int64_t)img * a.OH + oh) * a.OW + ow) * a.N + nb;       // of THIS lane's row
-                    if (resid && valid) {                           // the residual of the pass behind this one -> L2 while this one is computed
-                        const float *nx = nt + 1 < d.nt ? a.residual + orow + DBN
-                                                        : a.residual + orow - nb + (int64_t)gridDim.x * (DT * 128) * a.N;     // (1x1 layers: row = slot)
-                        if (nt + 1 < d.nt || (a.KH * a.KW == 1 && tile + (int)gridDim.x < d.n_tiles && (int64_t)slot + (int64_t)gridDim.x * (DT * 128) < a.M)) {
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 32));
-                        }
-                    }
-                    {
-                        float *dst = a.out + orow;
-                        const uint4 *res = resid ? reinterpret_cast<const uint4 *>(a.residual + orow) : nullptr;
+                    valid = img < (uint32_t)d.n_img && oh < (uint32_t)a.OH && ow < (uint32_t)a.OW;
+                    orow = (((int64_t)img * a.OH + oh) * a.OW + ow) * a.N + nb;
+                };
+                if (!resid) {
+                    if (lane == 0) mbar_wait(&sm->acc_full[abuf], ause, 5);
+                    __syncwarp();
+                    tc_fence_after();
 #pragma unroll 1
-                        for (int c = 0; c < DBN && nb + c < a.N; c += 32) {       // (N = 32: only the first 32 columns exist)
+                    for (int t = t_first; t < t_last; ++t) {
+                        geometry(t);
+                        float *dst = a.out + orow;
+                        const u32x8 none = {};
+#pragma unroll 1
+                        for (int c = 0; c < ncol; c += 32) {
                             uint32_t acc[32];
                             {
                                 uint32_t corr[32];
@@ -287,38 +298,57 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d)
                                 for (int q = 0; q < 32; ++q) acc[q] = __float_as_uint(__uint_as_float(acc[q]) + __uint_as_float(corr[q]));
                             }
                             if (valid) {
-                                u32x8 rw[4];                         // 32 channels of residual: four 32-byte loads
-                                if (resid) {
 #pragma unroll
-                                    for (int j = 0; j < 4; ++j) rw[j] = ldg256(res + (c >> 2) + 2 * j);
+                                for (int j = 0; j < 4; ++j) finish8(acc + 8 * j, none, nb + c + 8 * j, dst + c + 8 * j);
+                            }
+                        }
+                    }
+                } else {
+                    // The residual layers are bound by memory latency (profiles/r02_resnet_tc4h_full.txt: 2.6 TB/s, neither HBM
+                    // nor tensor bound): the residual words of a 16-channel chunk are requested one chunk ahead of their use --
+                    // the first chunk's BEFORE the accumulators are awaited -- so a round trip to L2 / HBM overlaps the TMEM
+                    // loads and the arithmetic of the chunk in front instead of following them.  16-column chunks keep two
+                    // chunks of residual words + one of accumulators inside the 128-register budget.
+                    u32x8 rw[2][2];
+                    auto request = [&](u32x8 (&r)[2], int c) {
+                        const uint4 *res = reinterpret_cast<const uint4 *>(a.residual + orow + c);
+                        r[0] = ldg256(res); r[1] = ldg256(res + 2);
+                    };
+                    geometry(t_first);
+                    if (valid) request(rw[0], 0);
+                    if (lane == 0) mbar_wait(&sm->acc_full[abuf], ause, 5);
+                    __syncwarp();
+                    tc_fence_after();
+#pragma unroll 1
+                    for (int t = t_first; t < t_last; ++t) {
+                        if (t != t_first) { geometry(t); if (valid) request(rw[0], 0); }
+                        if (valid) {                                // the residual of the pass behind this one -> L2 while this one is computed
+                            const float *nx = nt + 1 < d.nt ? a.residual + orow + DBN
+                                                            : a.residual + orow - nb + (int64_t)gridDim.x * (DT * 128) * a.N;     // (1x1 layers: row = slot)
+                            if (nt + 1 < d.nt || (a.KH * a.KW == 1 && tile + (int)gridDim.x < d.n_tiles && (int64_t)slot + (int64_t)gridDim.x * (DT * 128) < a.M)) {
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 32));
+                            }
+                        }
+                        float *dst = a.out + orow;
+                        const uint32_t col = tmem_base + lane_addr + abuf * 256u + (uint32_t)t * 128u;
+#pragma unroll
+                        for (int ci = 0; ci < DBN / 16; ++ci) {
+                            const int c = 16 * ci;
+                            if (c < ncol) {
+                                uint32_t acc[16];
+                                {
+                                    uint32_t corr[16];
+                                    tmem_ld16(col + (uint32_t)c, acc);
+                                    tmem_ld16(col + (uint32_t)c + DBN, corr);
+                                    tmem_ld_wait();
+#pragma unroll
+                                    for (int q = 0; q < 16; ++q) acc[q] = __float_as_uint(__uint_as_float(acc[q]) + __uint_as_float(corr[q]));
                                 }
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    float y[8];
-#pragma unroll
-                                    for (int h = 0; h < 2; ++h) {
-                                        float k1[4], k0[4], s2[4], t2[4];
-                                        const uint32_t cj = cst_u32 + 4u * (uint32_t)(nb + c + 8 * j + 4 * h);   // constants of channels nb + c + 8j + 4h ..
-                                        lds_f4(cj, k1); lds_f4(cj + cst_arr, k0);
-                                        if (post) { lds_f4(cj + 2u * cst_arr, s2); lds_f4(cj + 3u * cst_arr, t2); }
-#pragma unroll
-                                        for (int q = 0; q < 4; ++q) {
-                                            float v = fmaf(__uint_as_float(acc[8 * j + 4 * h + q]), k1[q], k0[q]);
-                                            if (resid) v += a.residual_packed ? iss_unpack_split(rw[j].v[4 * h + q]) : __uint_as_float(rw[j].v[4 * h + q]);
-                                            if (relu) v = fmaxf(v, 0.f);
-                                            if (post) v = fmaf(v, s2[q], t2[q]);
-                                            y[4 * h + q] = v;
-                                        }
-                                    }
-                                    u32x8 w;
-                                    if (a.out_packed) {
-#pragma unroll
-                                        for (int q = 0; q < 4; ++q) iss_pack_split2(y[2 * q], y[2 * q + 1], w.v[2 * q], w.v[2 * q + 1]);
-                                    } else {
-#pragma unroll
-                                        for (int q = 0; q < 8; ++q) w.v[q] = __float_as_uint(y[q]);
-                                    }
-                                    stg256(dst + c + 8 * j, w);
+                                if (valid && c + 16 < ncol) request(rw[(ci + 1) & 1], c + 16);
+                                if (valid) {
+                                    finish8(acc, rw[ci & 1][0], nb + c, dst + c);
+                                    finish8(acc + 8, rw[ci & 1][1], nb + c + 8, dst + c + 8);
                                 }
                             }
                         }
@@ -609,8 +639,6 @@ int iss_launch_conv_tc_f16d(ConvArgs &a, cudaStream_t st)
     d.bn_img = iss_f16_bn_for(a.N == 32 ? 64 : a.N);                     // tiling of the weight image (iss_prepare_f16_weights)
     const char *nepi_env = getenv("ISS_B200_NEPI");                      // A/B runs: 4 or 8
     d.n_epi = nepi_env ? (atoi(nepi_env) == 8 ? 8 : 4) : ((a.flags & ISS_F_RESIDUAL) ? 8 : 4);
-    const char *ord_env = getenv("ISS_B200_MMA_ORDER");
-    d.mma_order = ord_env && ord_env[0] == '1' ? 1 : 0;
     const int64_t total_slots = ((int64_t)(d.n_img - 1) * a.H + a.OH - 1) * a.W + a.OW;
     d.n_tiles = (int)((total_slots + DT * 128 - 1) / (DT * 128));
     int dev = 0, sms = 0;

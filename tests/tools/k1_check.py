@@ -1,14 +1,14 @@
 #!/usr/bin/env python
 """K1 (sidekit features) on the GPU: accuracy against the numpy oracle (pinned bit-for-bit to sidekit_mfcc.py) on a
 60 s synthetic clip + the committed media, and throughput on N hours of synthetic int16 PCM (CUDA events).
-   python tools/k1_check.py [hours=10]"""
+   python tests/tools/k1_check.py [hours=10]"""
 import os
 import sys
 
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import bench                                                               # noqa: E402
