@@ -64,11 +64,13 @@ struct Smem {
     float fbw[ISS_FB_MAXNNZ];
     int task_lo[32], task_cnt[32], task_off[32];      // mel tasks: bins [lo, lo + cnt) with weights fbw[off ..]
     int filt_first[ISS_NMEL], filt_n[ISS_NMEL];      // filter m = tasks [first, first + n)
-    Cplx<T> buf[NWARP][FFT_BUF];            // per-warp transpose rows of the FFT
-    float pw[NWARP][ZPAD];
-    T part[NWARP][32];                      // per-task partial mel sums
+    // per warp: the FFT's transpose rows; once the FFT is done the same bytes hold the power spectrum (ZPAD floats) and,
+    // behind it, the per-task partial mel sums (32 T) -- keeps the CTA at 3 per SM (a separate pw / part array costs
+    // 11 KB and drops it to 2)
+    Cplx<T> buf[NWARP][FFT_BUF];
     double red[NWARP][2];
 };
+static_assert(ZPAD * sizeof(float) + 32 * sizeof(double) <= FFT_BUF * 2 * sizeof(float), "pw + part must fit the transpose buffer");
 
 __device__ __forceinline__ int bitrev2(int r) { return ((r & 1) << 1) | ((r >> 1) & 1); }
 
@@ -132,9 +134,9 @@ sidekit_features_kernel(const void *__restrict__ pcm, int64_t n_samples, int64_t
     __syncthreads();
 
     Cplx<T> *buf = S.buf[warp];
-    float *pw = S.pw[warp];
+    float *pw = reinterpret_cast<float *>(buf);                      // valid between the FFT's last __syncwarp and the next frame
     double acc_sum = 0.0, acc_cnt = 0.0;
-    T *part = S.part[warp];
+    T *part = reinterpret_cast<T *>(reinterpret_cast<unsigned char *>(buf) + ZPAD * sizeof(float));
     // After the FFT this lane holds Z[k], k = zk1 + 8 a + 64 zk2b, in register a.  The split needs Z[256 - k]: it sits in
     // lane (8 - zk1) | (3 - r) at register 7 - a; for zk1 = 0 in lane 3 - r at register 8 - a, and for zk1 = 0, a = 0
     // (k = 0, 128, 64, 192) in lane {0, 1, 3, 2}[r].  Partners are always of the same class (zk1 = 0 or not), so the
@@ -214,12 +216,15 @@ sidekit_features_kernel(const void *__restrict__ pcm, int64_t n_samples, int64_t
         {
             const int lo = S.task_lo[lane], cnt = S.task_cnt[lane];
             const float *w = S.fbw + S.task_off[lane];
-            T acc = (T)0;
-            for (int b = 0; b < cnt; ++b) {
-                const int k = lo + b;
-                acc += (T)pw[k + 8 * (k >> 6)] * (T)w[b];
+            T acc0 = (T)0, acc1 = (T)0;                              // two chains: the kernel is latency-bound
+            int b = 0;
+            for (; b + 1 < cnt; b += 2) {
+                const int k = lo + b, k2 = k + 1;
+                acc0 += (T)pw[k + 8 * (k >> 6)] * (T)w[b];
+                acc1 += (T)pw[k2 + 8 * (k2 >> 6)] * (T)w[b + 1];
             }
-            part[lane] = acc;
+            if (b < cnt) { const int k = lo + b; acc0 += (T)pw[k + 8 * (k >> 6)] * (T)w[b]; }
+            part[lane] = acc0 + acc1;
         }
         __syncwarp();
         if (lane < ISS_NMEL) {
