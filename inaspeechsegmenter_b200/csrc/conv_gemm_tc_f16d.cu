@@ -70,6 +70,7 @@ struct DirectArgs {
     int nt;                     // 64-channel n-tiles (N / 64)
     int bn_img;                 // n-tile width of the weight image (64 or 128, iss_f16_bn_for)
     int n_epi;                  // epilogue warps: 4 (one per TMEM lane quadrant, both sub-tiles) or 8 (one per quadrant and sub-tile)
+    int res_pipe;               // residual layers: request the residual words one 16-column chunk ahead (ISS_B200_RES_PIPE=0: A/B runs)
 };
 
 __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
@@ -277,7 +278,7 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d)
                     valid = img < (uint32_t)d.n_img && oh < (uint32_t)a.OH && ow < (uint32_t)a.OW;
                     orow = (((int64_t)img * a.OH + oh) * a.OW + ow) * a.N + nb;
                 };
-                if (!resid) {
+                if (!resid || !d.res_pipe) {
                     if (lane == 0) mbar_wait(&sm->acc_full[abuf], ause, 5);
                     __syncwarp();
                     tc_fence_after();
@@ -285,7 +286,7 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d)
                     for (int t = t_first; t < t_last; ++t) {
                         geometry(t);
                         float *dst = a.out + orow;
-                        const u32x8 none = {};
+                        const uint4 *res = resid ? reinterpret_cast<const uint4 *>(a.residual + orow) : nullptr;
 #pragma unroll 1
                         for (int c = 0; c < ncol; c += 32) {
                             uint32_t acc[32];
@@ -298,8 +299,13 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d)
                                 for (int q = 0; q < 32; ++q) acc[q] = __float_as_uint(__uint_as_float(acc[q]) + __uint_as_float(corr[q]));
                             }
                             if (valid) {
+                                u32x8 rw[4] = {};                    // 32 channels of residual: four 32-byte loads
+                                if (resid) {
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) finish8(acc + 8 * j, none, nb + c + 8 * j, dst + c + 8 * j);
+                                    for (int j = 0; j < 4; ++j) rw[j] = ldg256(res + (c >> 2) + 2 * j);
+                                }
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) finish8(acc + 8 * j, rw[j], nb + c + 8 * j, dst + c + 8 * j);
                             }
                         }
                     }
@@ -639,6 +645,8 @@ int iss_launch_conv_tc_f16d(ConvArgs &a, cudaStream_t st)
     d.bn_img = iss_f16_bn_for(a.N == 32 ? 64 : a.N);                     // tiling of the weight image (iss_prepare_f16_weights)
     const char *nepi_env = getenv("ISS_B200_NEPI");                      // A/B runs: 4 or 8
     d.n_epi = nepi_env ? (atoi(nepi_env) == 8 ? 8 : 4) : ((a.flags & ISS_F_RESIDUAL) ? 8 : 4);
+    const char *rp_env = getenv("ISS_B200_RES_PIPE");
+    d.res_pipe = rp_env && rp_env[0] == '0' ? 0 : 1;
     const int64_t total_slots = ((int64_t)(d.n_img - 1) * a.H + a.OH - 1) * a.W + a.OW;
     d.n_tiles = (int)((total_slots + DT * 128 - 1) / (DT * 128));
     int dev = 0, sms = 0;

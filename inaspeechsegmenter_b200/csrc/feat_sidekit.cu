@@ -82,7 +82,8 @@ sidekit_features_kernel(const void *__restrict__ pcm, int64_t n_samples, int64_t
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem<T, PCM> &S = *reinterpret_cast<Smem<T, PCM> *>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // (a value the compiler knows to be warp-uniform: no re-convergence code around the frame loop's shuffles)
     const int64_t f0 = (int64_t)blockIdx.x * FR;
     const int64_t s0 = f0 * ISS_HOP;
     const int nfr = (int)min((int64_t)FR, n_frames - f0);
