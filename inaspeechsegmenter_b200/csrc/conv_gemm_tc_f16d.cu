@@ -37,6 +37,7 @@
 #include <cuda_fp16.h>
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "tc_common.cuh"
 
@@ -57,6 +58,8 @@ constexpr int D_TAB = 8;                                // images a slab may tou
 constexpr int D_SMEM_MAX = 232448;
 
 constexpr int DIN_PACKED = 1, DIN_FIRST = 2, DIN_POOL = 3, DIN_F32 = 4;
+constexpr int D_RES_BOX = 128 * 128;                    // one residual / output box: 128 rows x 32 channels (128 B, SWIZZLE_128B)
+constexpr int D_RES_MAX = 4;                            // boxes in the ring at most
 
 struct DirectArgs {
     const unsigned char *wt;    // tiled fp16 image [k-block][hi | lo][64 rows x 128 B, SWIZZLE_128B]
@@ -70,8 +73,11 @@ struct DirectArgs {
     int nt;                     // 64-channel n-tiles (N / 64)
     int bn_img;                 // n-tile width of the weight image (64 or 128, iss_f16_bn_for)
     int n_epi;                  // epilogue warps: 4 (one per TMEM lane quadrant, both sub-tiles) or 8 (one per quadrant and sub-tile)
-    int res_pipe;               // residual layers: request the residual words one 16-column chunk ahead (ISS_B200_RES_PIPE=0: A/B runs)
+    int tma;                    // residual 1x1 layers: bit 0 = residual boxes by tensor-map TMA (cp.async.bulk.tensor), bit 1 = outputs by TMA store
+    int rs;                     // boxes in the residual ring (2 .. D_RES_MAX)
 };
+// tensor maps of the residual and the output tensor ([M rows][N words], box 32 words x 128 rows, SWIZZLE_128B); zero when unused
+struct alignas(64) DirectMaps { CUtensorMap res, out; };
 
 __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
 {
@@ -99,11 +105,29 @@ __device__ __forceinline__ void lds_f4(uint32_t addr, float (&v)[4])
 struct DSmem {                                           // everything behind the 1024-aligned operand buffers
     long long tab_row[2][D_TAB];                         // IN_FIRST: Y row of input row 0 of the images a slab touches (-1: none)
     uint64_t slab_full[2], slab_empty[2], acc_full[2], acc_empty[2], b_full[DSB], b_empty[DSB];
+    uint64_t res_full[D_RES_MAX], res_empty[D_RES_MAX];  // residual boxes (TMA mode)
     uint32_t tmem_slot;
 };
+
+__device__ __forceinline__ void lds128(uint32_t addr, uint32_t &x, uint32_t &y, uint32_t &z, uint32_t &w)
+{
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "r"(addr) : "memory");
+}
+// one box of a [rows][words] tensor -> shared memory, completion on an mbarrier (UTMALDG)
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+// one box shared memory -> tensor (UTMASTG), bulk async-group completion
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
 template <int MODE, int NBUF>
 __global__ void __launch_bounds__(D_THREADS, 1)
-conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d)
+conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d, const __grid_constant__ DirectMaps maps)
 {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -111,10 +135,12 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d)
     unsigned char *b_ring = smem;
     unsigned char *slab = smem + DSB * D_B_STAGE;         // [NBUF buffers][channel block][hi plane | lo plane]
     const uint32_t slab_buf = 2u * (uint32_t)d.cb * plane;
-    DSmem *sm = reinterpret_cast<DSmem *>(slab + (size_t)NBUF * slab_buf);
+    unsigned char *res_ring = slab + (size_t)NBUF * slab_buf;          // [d.rs boxes] (TMA mode only), 1024-aligned
+    DSmem *sm = reinterpret_cast<DSmem *>(res_ring + (d.tma ? (size_t)d.rs * D_RES_BOX : 0));
     // k1 | k0 | es2 | et2, N floats each (y = acc * k1 + k0, ReLU, y * es2 + et2); 16-byte aligned for the epilogue's LDS.128
     float *cst = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(sm + 1) + 15) & ~(uintptr_t)15);
-    const int n_fill_warps = D_WARPS - 2 - d.n_epi, first_fill = 2 + d.n_epi, nfill = 32 * n_fill_warps;
+    // TMA mode: the last warp feeds the residual ring instead of filling the slab
+    const int n_fill_warps = D_WARPS - 2 - d.n_epi - (d.tma ? 1 : 0), first_fill = 2 + d.n_epi, nfill = 32 * n_fill_warps;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nkb = a.KH * a.KW * d.cb;                   // k-block = 64 channels of one filter tap
@@ -126,6 +152,8 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d)
             mbar_init(&sm->acc_full[b], 1); mbar_init(&sm->acc_empty[b], d.n_epi);
         }
         for (int s = 0; s < DSB; ++s) { mbar_init(&sm->b_full[s], 1); mbar_init(&sm->b_empty[s], 1); }
+        // a box is released by the 4 warps that read it, or (outputs by TMA store) by the one thread that stored it
+        for (int s = 0; s < D_RES_MAX; ++s) { mbar_init(&sm->res_full[s], 1); mbar_init(&sm->res_empty[s], (d.tma & 2) ? 1 : 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -235,8 +263,8 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d)
         // layers are bound by memory latency x bytes in flight, not by instructions)
         const int t_first = d.n_epi == 8 ? ((warp - 2) >> 2) : 0, t_last = d.n_epi == 8 ? t_first + 1 : DT;
         const uint32_t cst_u32 = smem_u32(cst), cst_arr = 4u * (uint32_t)a.N;         // byte address of the table, bytes per array
-        // 8 channels (n0 ..) of this lane's row: bias/BN affine (+ residual words rw) / ReLU / second affine -> 32 bytes to HBM
-        auto finish8 = [&](const uint32_t *acc, const u32x8 &rw, int n0, float *dst) {
+        // 8 channels (n0 ..) of this lane's row: bias/BN affine (+ residual words rw) / ReLU / second affine -> 8 output words
+        auto finish8 = [&](const uint32_t *acc, const u32x8 &rw, int n0) -> u32x8 {
             float y[8];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -261,8 +289,13 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d)
 #pragma unroll
                 for (int q = 0; q < 8; ++q) w.v[q] = __float_as_uint(y[q]);
             }
-            stg256(dst, w);
+            return w;
         };
+        // TMA mode (residual 1x1 layers, 8 epilogue warps): the residual words of (pass, 32-channel half h, sub-tile t) arrive as
+        // box 2 * chunk + t of a ring fed by the last warp; with bit 1 the outputs are written back in place and leave by TMA store
+        const bool tma = d.tma != 0, tma_st = (d.tma & 2) != 0;
+        const uint32_t res_u32 = smem_u32(res_ring);
+        uint32_t chunk = 0;                                   // running (tile, pass, half) count of this CTA
         uint32_t p = 0;
         for (int tile = blockIdx.x; tile < d.n_tiles; tile += gridDim.x) {
             for (int nt = 0; nt < d.nt; ++nt, ++p) {
@@ -278,91 +311,119 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d)
                     valid = img < (uint32_t)d.n_img && oh < (uint32_t)a.OH && ow < (uint32_t)a.OW;
                     orow = (((int64_t)img * a.OH + oh) * a.OW + ow) * a.N + nb;
                 };
-                if (!resid || !d.res_pipe) {
-                    if (lane == 0) mbar_wait(&sm->acc_full[abuf], ause, 5);
-                    __syncwarp();
-                    tc_fence_after();
+                if (lane == 0) mbar_wait(&sm->acc_full[abuf], ause, 5);
+                __syncwarp();
+                tc_fence_after();
 #pragma unroll 1
-                    for (int t = t_first; t < t_last; ++t) {
-                        geometry(t);
-                        float *dst = a.out + orow;
-                        const uint4 *res = resid ? reinterpret_cast<const uint4 *>(a.residual + orow) : nullptr;
-#pragma unroll 1
-                        for (int c = 0; c < ncol; c += 32) {
-                            uint32_t acc[32];
-                            {
-                                uint32_t corr[32];
-                                const uint32_t col = tmem_base + lane_addr + abuf * 256u + (uint32_t)t * 128u + (uint32_t)c;
-                                tmem_ld32(col, acc);
-                                tmem_ld32(col + DBN, corr);
-#pragma unroll
-                                for (int q = 0; q < 32; ++q) acc[q] = __float_as_uint(__uint_as_float(acc[q]) + __uint_as_float(corr[q]));
-                            }
-                            if (valid) {
-                                u32x8 rw[4] = {};                    // 32 channels of residual: four 32-byte loads
-                                if (resid) {
-#pragma unroll
-                                    for (int j = 0; j < 4; ++j) rw[j] = ldg256(res + (c >> 2) + 2 * j);
-                                }
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) finish8(acc + 8 * j, rw[j], nb + c + 8 * j, dst + c + 8 * j);
-                            }
+                for (int t = t_first; t < t_last; ++t) {
+                    geometry(t);
+                    if (resid && valid && !tma) {                   // the residual of the pass behind this one -> L2 while this one is computed
+                        const float *nx = nt + 1 < d.nt ? a.residual + orow + DBN
+                                                        : a.residual + orow - nb + (int64_t)gridDim.x * (DT * 128) * a.N;     // (1x1 layers: row = slot)
+                        if (nt + 1 < d.nt || (a.KH * a.KW == 1 && tile + (int)gridDim.x < d.n_tiles && (int64_t)slot + (int64_t)gridDim.x * (DT * 128) < a.M)) {
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 32));
                         }
                     }
-                } else {
-                    // The residual layers are bound by memory latency (profiles/r02_resnet_tc4h_full.txt: 2.6 TB/s, neither HBM
-                    // nor tensor bound): the residual words of a 16-channel chunk are requested one chunk ahead of their use --
-                    // the first chunk's BEFORE the accumulators are awaited -- so a round trip to L2 / HBM overlaps the TMEM
-                    // loads and the arithmetic of the chunk in front instead of following them.  16-column chunks keep two
-                    // chunks of residual words + one of accumulators inside the 128-register budget.
-                    u32x8 rw[2][2];
-                    auto request = [&](u32x8 (&r)[2], int c) {
-                        const uint4 *res = reinterpret_cast<const uint4 *>(a.residual + orow + c);
-                        r[0] = ldg256(res); r[1] = ldg256(res + 2);
-                    };
-                    geometry(t_first);
-                    if (valid) request(rw[0], 0);
-                    if (lane == 0) mbar_wait(&sm->acc_full[abuf], ause, 5);
-                    __syncwarp();
-                    tc_fence_after();
+                    float *dst = a.out + orow;
+                    const uint4 *res = resid ? reinterpret_cast<const uint4 *>(a.residual + orow) : nullptr;
+                    const int64_t row0 = (int64_t)tile * (DT * 128) + (int64_t)t * 128;          // first row of the sub-tile (1x1: row = slot)
 #pragma unroll 1
-                    for (int t = t_first; t < t_last; ++t) {
-                        if (t != t_first) { geometry(t); if (valid) request(rw[0], 0); }
-                        if (valid) {                                // the residual of the pass behind this one -> L2 while this one is computed
-                            const float *nx = nt + 1 < d.nt ? a.residual + orow + DBN
-                                                            : a.residual + orow - nb + (int64_t)gridDim.x * (DT * 128) * a.N;     // (1x1 layers: row = slot)
-                            if (nt + 1 < d.nt || (a.KH * a.KW == 1 && tile + (int)gridDim.x < d.n_tiles && (int64_t)slot + (int64_t)gridDim.x * (DT * 128) < a.M)) {
-                                asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
-                                asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 32));
-                            }
+                    for (int c = 0; c < ncol; c += 32) {
+                        uint32_t acc[32];
+                        {
+                            uint32_t corr[32];
+                            const uint32_t col = tmem_base + lane_addr + abuf * 256u + (uint32_t)t * 128u + (uint32_t)c;
+                            tmem_ld32(col, acc);
+                            tmem_ld32(col + DBN, corr);
+#pragma unroll
+                            for (int q = 0; q < 32; ++q) acc[q] = __float_as_uint(__uint_as_float(acc[q]) + __uint_as_float(corr[q]));
                         }
-                        float *dst = a.out + orow;
-                        const uint32_t col = tmem_base + lane_addr + abuf * 256u + (uint32_t)t * 128u;
+                        if (tma) {
+                            const uint32_t ck = chunk + (uint32_t)(c >> 5);
+                            {
+                                const uint32_t g = 2u * ck + (uint32_t)t, sl = g % (uint32_t)d.rs, use = g / (uint32_t)d.rs;
+                                mbar_wait(&sm->res_full[sl], use & 1u, 8);      // every reading thread observes the completion itself
+                                // this lane's row of the box: 128 bytes, 16-byte chunk q at q ^ (row & 7) (SWIZZLE_128B)
+                                const uint32_t r = (uint32_t)(quad * 32 + lane);
+                                const uint32_t rowa = res_u32 + sl * (uint32_t)D_RES_BOX + r * 128u, x7 = r & 7u;
+                                u32x8 rw[4];
 #pragma unroll
-                        for (int ci = 0; ci < DBN / 16; ++ci) {
-                            const int c = 16 * ci;
-                            if (c < ncol) {
-                                uint32_t acc[16];
-                                {
-                                    uint32_t corr[16];
-                                    tmem_ld16(col + (uint32_t)c, acc);
-                                    tmem_ld16(col + (uint32_t)c + DBN, corr);
-                                    tmem_ld_wait();
-#pragma unroll
-                                    for (int q = 0; q < 16; ++q) acc[q] = __float_as_uint(__uint_as_float(acc[q]) + __uint_as_float(corr[q]));
+                                for (int j = 0; j < 4; ++j) {
+                                    lds128(rowa + (((uint32_t)(2 * j) ^ x7) << 4), rw[j].v[0], rw[j].v[1], rw[j].v[2], rw[j].v[3]);
+                                    lds128(rowa + (((uint32_t)(2 * j + 1) ^ x7) << 4), rw[j].v[4], rw[j].v[5], rw[j].v[6], rw[j].v[7]);
                                 }
-                                if (valid && c + 16 < ncol) request(rw[(ci + 1) & 1], c + 16);
-                                if (valid) {
-                                    finish8(acc, rw[ci & 1][0], nb + c, dst + c);
-                                    finish8(acc + 8, rw[ci & 1][1], nb + c + 8, dst + c + 8);
+                                if (!tma_st) {
+                                    __syncwarp();
+                                    if (lane == 0) mbar_arrive(&sm->res_empty[sl]);          // 4 warps read a box
+                                    if (valid) {
+#pragma unroll
+                                        for (int j = 0; j < 4; ++j) stg256(dst + c + 8 * j, finish8(acc + 8 * j, rw[j], nb + c + 8 * j));
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        const u32x8 w = finish8(acc + 8 * j, rw[j], nb + c + 8 * j);
+                                        sts128(rowa + (((uint32_t)(2 * j) ^ x7) << 4), w.v[0], w.v[1], w.v[2], w.v[3]);
+                                        sts128(rowa + (((uint32_t)(2 * j + 1) ^ x7) << 4), w.v[4], w.v[5], w.v[6], w.v[7]);
+                                    }
+                                    fence_proxy_async();             // generic-proxy stores -> visible to the TMA store
+                                    asm volatile("bar.sync %0, 128;" ::"r"(2 + t) : "memory");           // the 4 warps of this sub-tile
+                                    if ((warp & 3) == 2 && lane == 0) {   // (warps 2 and 6 are the first of their groups)
+                                        if (row0 < a.M) {            // rows behind the last one are clipped by the TMA unit
+                                            tma_store_2d(&maps.out, res_u32 + sl * (uint32_t)D_RES_BOX, nb + c, (int)row0);
+                                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                                            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the box has been read: it may be refilled
+                                        }
+                                        mbar_arrive(&sm->res_empty[sl]);
+                                    }
                                 }
                             }
+                        } else if (valid) {
+                            // (requesting the residual words one chunk ahead of use -- the first chunk's before the accumulators are
+                            //  awaited -- measured 0.4 % SLOWER on ResNet101, r02n: the residual layers are not bound by this latency)
+                            u32x8 rw[4] = {};                        // 32 channels of residual: four 32-byte loads
+                            if (resid) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) rw[j] = ldg256(res + (c >> 2) + 2 * j);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) stg256(dst + c + 8 * j, finish8(acc + 8 * j, rw[j], nb + c + 8 * j));
                         }
                     }
                 }
+                chunk += (uint32_t)(ncol >> 5);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm->acc_empty[abuf]);
+            }
+        }
+        if (tma_st) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // every TMA store of this thread has completed
+    } else if (d.tma && warp == D_WARPS - 1) {
+        // ============================ residual boxes (TMA mode) ============================
+        // order = the consumers': per (tile, pass, 32-channel half) one box per sub-tile; the ring bounds how far this runs ahead
+        uint32_t g = 0;
+        const uint32_t res_u32 = smem_u32(res_ring);
+        for (int tile = blockIdx.x; tile < d.n_tiles; tile += gridDim.x) {
+            for (int nt = 0; nt < d.nt; ++nt) {
+                const int nb = nt * DBN;
+                const int ncol = a.N - nb < DBN ? a.N - nb : DBN;
+                for (int c = 0; c < ncol; c += 32) {
+                    for (int t = 0; t < DT; ++t, ++g) {
+                        // (a sub-tile wholly behind the last row still gets a box -- rows 0.. of the tensor, never used -- so that
+                        //  box indices, ring slots and barrier phases stay in step on both sides)
+                        int64_t row0 = (int64_t)tile * (DT * 128) + (int64_t)t * 128;
+                        if (row0 >= a.M) row0 = 0;
+                        const uint32_t sl = g % (uint32_t)d.rs, use = g / (uint32_t)d.rs;
+                        mbar_wait(&sm->res_empty[sl], (use & 1u) ^ 1u, 7);
+                        if (elect_one()) {
+                            const uint32_t bar = smem_u32(&sm->res_full[sl]);
+                            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)D_RES_BOX) : "memory");
+                            tma_load_2d(res_u32 + sl * (uint32_t)D_RES_BOX, &maps.res, nb + c, (int)row0, bar);
+                        }
+                        __syncwarp();
+                    }
+                }
             }
         }
     } else {
@@ -593,12 +654,50 @@ int direct_nbuf(const ConvArgs &a)
     return 0;
 }
 
+// ---- tensor maps for the TMA mode of the residual layers -------------------------------------------------------------
+// cuTensorMapEncodeTiled is a driver entry point: fetched through the runtime so that the library does not link libcuda
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled()
+{
+    static const EncodeTiledFn fn = [] {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+// [rows][n] 32-bit words, box = 32 words (128 bytes, SWIZZLE_128B) x 128 rows; elements behind the last row read as zero and
+// are not written
+bool make_rows_map(CUtensorMap *m, const void *base, int64_t rows, int n)
+{
+    const EncodeTiledFn enc = encode_tiled();
+    if (!enc || (reinterpret_cast<uintptr_t>(base) & 15) != 0 || n % 32 != 0) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)n * 4};
+    const cuuint32_t box[2] = {32, 128}, estr[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int MODE, int NBUF>
-int launch_tc4h(const ConvArgs &a, const FirstFuse &ff, const DirectArgs &d, unsigned grid, cudaStream_t st)
+int launch_tc4h(const ConvArgs &a, const FirstFuse &ff, DirectArgs d, unsigned grid, cudaStream_t st)
 {
     auto kern = conv_gemm_tc4h_kernel<MODE, NBUF>;
     ISS_CUDA_OK(iss_optin_smem(reinterpret_cast<const void *>(kern), D_SMEM_MAX));
-    kern<<<grid, D_THREADS, direct_smem(a, NBUF), st>>>(a, ff, d);
+    DirectMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    size_t smem = direct_smem(a, NBUF);
+    if (d.tma) {
+        // the ring takes what is left of the shared memory: at least 2 boxes, else the mode is off for this layer
+        const int fit = (int)(((size_t)D_SMEM_MAX - smem) / D_RES_BOX);
+        d.rs = fit < D_RES_MAX ? fit : D_RES_MAX;
+        if (d.rs < 2 || !make_rows_map(&maps.res, a.residual, a.M, a.N) || ((d.tma & 2) && !make_rows_map(&maps.out, a.out, a.M, a.N))) { d.tma = 0; d.rs = 0; }
+        else smem += (size_t)d.rs * D_RES_BOX;
+    }
+    kern<<<grid, D_THREADS, smem, st>>>(a, ff, d, maps);
     ISS_CUDA_OK(cudaGetLastError());
     iss_count_launch();
     return ISS_OK;
@@ -645,8 +744,13 @@ int iss_launch_conv_tc_f16d(ConvArgs &a, cudaStream_t st)
     d.bn_img = iss_f16_bn_for(a.N == 32 ? 64 : a.N);                     // tiling of the weight image (iss_prepare_f16_weights)
     const char *nepi_env = getenv("ISS_B200_NEPI");                      // A/B runs: 4 or 8
     d.n_epi = nepi_env ? (atoi(nepi_env) == 8 ? 8 : 4) : ((a.flags & ISS_F_RESIDUAL) ? 8 : 4);
-    const char *rp_env = getenv("ISS_B200_RES_PIPE");
-    d.res_pipe = rp_env && rp_env[0] == '0' ? 0 : 1;
+    // TMA mode of the residual 1x1 layers (ISS_B200_TMA_EPI: 0 off, 1 residual boxes by TMA, 3 + outputs by TMA store)
+    {
+        const char *te = getenv("ISS_B200_TMA_EPI");
+        const int want = te ? atoi(te) & 3 : 0;
+        const bool ok = (a.flags & ISS_F_RESIDUAL) && a.KH * a.KW == 1 && a.N % 32 == 0 && d.n_epi == 8 && !a.first && a.pool_h == 0;
+        d.tma = ok ? ((want & 1) ? want : 0) : 0;
+    }
     const int64_t total_slots = ((int64_t)(d.n_img - 1) * a.H + a.OH - 1) * a.W + a.OW;
     d.n_tiles = (int)((total_slots + DT * 128 - 1) / (DT * 128));
     int dev = 0, sms = 0;
