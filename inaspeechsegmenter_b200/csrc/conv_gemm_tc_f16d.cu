@@ -401,30 +401,55 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d, 
         if (tma_st) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // every TMA store of this thread has completed
     } else if (d.tma && warp == D_WARPS - 1) {
         // ============================ residual boxes (TMA mode) ============================
-        // order = the consumers': per (tile, pass, 32-channel half) one box per sub-tile; the ring bounds how far this runs ahead
-        uint32_t g = 0;
+        // order = the consumers': per (tile, pass, 32-channel half) one box per sub-tile.  The ring is short (2-4 boxes: what the
+        // slab leaves of the shared memory), so a second cursor runs D_RES_AHEAD boxes in front and pulls them into L2
+        // (cp.async.bulk.prefetch.tensor): the ring then turns over at L2 latency instead of HBM latency.
+        struct Cur { int tile, nt, c, t; };
+        auto box_of = [&](const Cur &k, int &c0, int &r0) {
+            // (a sub-tile wholly behind the last row still gets a box -- rows 0.. of the tensor, never used -- so that box
+            //  indices, ring slots and barrier phases stay in step on both sides)
+            int64_t row0 = (int64_t)k.tile * (DT * 128) + (int64_t)k.t * 128;
+            if (row0 >= a.M) row0 = 0;
+            c0 = k.nt * DBN + k.c; r0 = (int)row0;
+        };
+        auto advance = [&](Cur &k) {                                  // false behind the last box of this CTA
+            const int ncol = a.N - k.nt * DBN < DBN ? a.N - k.nt * DBN : DBN;
+            if (++k.t < DT) return true;
+            k.t = 0;
+            if ((k.c += 32) < ncol) return true;
+            k.c = 0;
+            if (++k.nt < d.nt) return true;
+            k.nt = 0;
+            return (k.tile += (int)gridDim.x) < d.n_tiles;
+        };
+        constexpr int D_RES_AHEAD = 8;
         const uint32_t res_u32 = smem_u32(res_ring);
-        for (int tile = blockIdx.x; tile < d.n_tiles; tile += gridDim.x) {
-            for (int nt = 0; nt < d.nt; ++nt) {
-                const int nb = nt * DBN;
-                const int ncol = a.N - nb < DBN ? a.N - nb : DBN;
-                for (int c = 0; c < ncol; c += 32) {
-                    for (int t = 0; t < DT; ++t, ++g) {
-                        // (a sub-tile wholly behind the last row still gets a box -- rows 0.. of the tensor, never used -- so that
-                        //  box indices, ring slots and barrier phases stay in step on both sides)
-                        int64_t row0 = (int64_t)tile * (DT * 128) + (int64_t)t * 128;
-                        if (row0 >= a.M) row0 = 0;
-                        const uint32_t sl = g % (uint32_t)d.rs, use = g / (uint32_t)d.rs;
-                        mbar_wait(&sm->res_empty[sl], (use & 1u) ^ 1u, 7);
-                        if (elect_one()) {
-                            const uint32_t bar = smem_u32(&sm->res_full[sl]);
-                            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)D_RES_BOX) : "memory");
-                            tma_load_2d(res_u32 + sl * (uint32_t)D_RES_BOX, &maps.res, nb + c, (int)row0, bar);
-                        }
-                        __syncwarp();
-                    }
-                }
+        Cur cur = {(int)blockIdx.x, 0, 0, 0}, pf = cur;
+        bool more = cur.tile < d.n_tiles, pf_more = more;
+        auto prefetch = [&]() {
+            if (!pf_more) return;
+            int c0, r0;
+            box_of(pf, c0, r0);
+            if (elect_one())
+                asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+                             ::"l"(reinterpret_cast<uint64_t>(&maps.res)), "r"(c0), "r"(r0) : "memory");
+            __syncwarp();
+            pf_more = advance(pf);
+        };
+        for (int i = 0; i < D_RES_AHEAD; ++i) prefetch();
+        for (uint32_t g = 0; more; ++g) {
+            const uint32_t sl = g % (uint32_t)d.rs, use = g / (uint32_t)d.rs;
+            int c0, r0;
+            box_of(cur, c0, r0);
+            mbar_wait(&sm->res_empty[sl], (use & 1u) ^ 1u, 7);
+            if (elect_one()) {
+                const uint32_t bar = smem_u32(&sm->res_full[sl]);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)D_RES_BOX) : "memory");
+                tma_load_2d(res_u32 + sl * (uint32_t)D_RES_BOX, &maps.res, c0, r0, bar);
             }
+            __syncwarp();
+            prefetch();
+            more = advance(cur);
         }
     } else {
         // ============================ slab fill ============================
