@@ -47,7 +47,8 @@ bool iss_conv_f16_direct_covers(const ConvArgs &a);
 namespace {
 
 constexpr int HBK = 64;
-constexpr int DT = 2;                                   // 128-slot sub-tiles per tile
+// (DT, the number of 128-slot sub-tiles per tile, is a template parameter of the kernel: 2, or 1 for the 1x1 layers whose
+//  two slab buffers only fit with 128-row tiles)
 constexpr int DSB = 3;                                  // weight stages
 constexpr int DBN = 64;                                 // output channels per pass (n-tile)
 constexpr int D_NMAX = 512;                             // output channels of a layer
@@ -125,7 +126,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t sr
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
-template <int MODE, int NBUF>
+template <int MODE, int NBUF, int DT>
 __global__ void __launch_bounds__(D_THREADS, 1)
 conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d, const __grid_constant__ DirectMaps maps)
 {
@@ -261,7 +262,11 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d, 
         const bool relu = a.flags & ISS_F_RELU, post = a.flags & ISS_F_AFFINE_POST, resid = a.flags & ISS_F_RESIDUAL;
         // 8 epilogue warps: warps 2-5 take sub-tile 0, warps 6-9 sub-tile 1 (twice the loads / stores in flight: the residual
         // layers are bound by memory latency x bytes in flight, not by instructions)
-        const int t_first = d.n_epi == 8 ? ((warp - 2) >> 2) : 0, t_last = d.n_epi == 8 ? t_first + 1 : DT;
+        // DT = 2: one group of four warps per sub-tile; DT = 1: the two groups split the 32-column chunks of the one sub-tile
+        const int egrp = d.n_epi == 8 ? ((warp - 2) >> 2) : 0;
+        const bool split_t = DT == 2 && d.n_epi == 8, split_c = DT == 1 && d.n_epi == 8;
+        const int t_first = split_t ? egrp : 0, t_last = split_t ? t_first + 1 : DT;
+        const int c_first = split_c ? 32 * egrp : 0, c_step = split_c ? 64 : 32;
         const uint32_t cst_u32 = smem_u32(cst), cst_arr = 4u * (uint32_t)a.N;         // byte address of the table, bytes per array
         // 8 channels (n0 ..) of this lane's row: bias/BN affine (+ residual words rw) / ReLU / second affine -> 8 output words
         auto finish8 = [&](const uint32_t *acc, const u32x8 &rw, int n0) -> u32x8 {
@@ -292,7 +297,7 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d, 
             return w;
         };
         // TMA mode (residual 1x1 layers, 8 epilogue warps): the residual words of (pass, 32-channel half h, sub-tile t) arrive as
-        // box 2 * chunk + t of a ring fed by the last warp; with bit 1 the outputs are written back in place and leave by TMA store
+        // box DT * chunk + t of a ring fed by the last warp; with bit 1 the outputs are written back in place and leave by TMA store
         const bool tma = d.tma != 0, tma_st = (d.tma & 2) != 0;
         const uint32_t res_u32 = smem_u32(res_ring);
         uint32_t chunk = 0;                                   // running (tile, pass, half) count of this CTA
@@ -329,7 +334,7 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d, 
                     const uint4 *res = resid ? reinterpret_cast<const uint4 *>(a.residual + orow) : nullptr;
                     const int64_t row0 = (int64_t)tile * (DT * 128) + (int64_t)t * 128;          // first row of the sub-tile (1x1: row = slot)
 #pragma unroll 1
-                    for (int c = 0; c < ncol; c += 32) {
+                    for (int c = c_first; c < ncol; c += c_step) {
                         uint32_t acc[32];
                         {
                             uint32_t corr[32];
@@ -342,7 +347,7 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d, 
                         if (tma) {
                             const uint32_t ck = chunk + (uint32_t)(c >> 5);
                             {
-                                const uint32_t g = 2u * ck + (uint32_t)t, sl = g % (uint32_t)d.rs, use = g / (uint32_t)d.rs;
+                                const uint32_t g = (uint32_t)DT * ck + (uint32_t)t, sl = g % (uint32_t)d.rs, use = g / (uint32_t)d.rs;
                                 mbar_wait(&sm->res_full[sl], use & 1u, 8);      // every reading thread observes the completion itself
                                 // this lane's row of the box: 128 bytes, 16-byte chunk q at q ^ (row & 7) (SWIZZLE_128B)
                                 const uint32_t r = (uint32_t)(quad * 32 + lane);
@@ -368,7 +373,7 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d, 
                                         sts128(rowa + (((uint32_t)(2 * j + 1) ^ x7) << 4), w.v[4], w.v[5], w.v[6], w.v[7]);
                                     }
                                     fence_proxy_async();             // generic-proxy stores -> visible to the TMA store
-                                    asm volatile("bar.sync %0, 128;" ::"r"(2 + t) : "memory");           // the 4 warps of this sub-tile
+                                    asm volatile("bar.sync %0, 128;" ::"r"(2 + egrp) : "memory");        // the 4 warps that share this box
                                     if ((warp & 3) == 2 && lane == 0) {   // (warps 2 and 6 are the first of their groups)
                                         if (row0 < a.M) {            // rows behind the last one are clipped by the TMA unit
                                             tma_store_2d(&maps.out, res_u32 + sl * (uint32_t)D_RES_BOX, nb + c, (int)row0);
@@ -655,28 +660,37 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d, 
     }
 }
 
-int direct_npix(const ConvArgs &a)
+int direct_npix(const ConvArgs &a, int dt)
 {
-    const int npix = DT * 128 + (a.KH - 1) * a.W + a.KW - 1;
+    const int npix = dt * 128 + (a.KH - 1) * a.W + a.KW - 1;
     return (npix + 7) & ~7;
 }
 
 int direct_cb(const ConvArgs &a) { return (a.C + HBK - 1) / HBK; }
 
-size_t direct_smem(const ConvArgs &a, int nbuf)
+size_t direct_smem(const ConvArgs &a, int nbuf, int dt)
 {
-    return (size_t)DSB * D_B_STAGE + (size_t)nbuf * 2 * direct_cb(a) * direct_npix(a) * 128 + sizeof(DSmem) + 1024 + 16 + (size_t)4 * a.N * sizeof(float);
+    return (size_t)DSB * D_B_STAGE + (size_t)nbuf * 2 * direct_cb(a) * direct_npix(a, dt) * 128 + sizeof(DSmem) + 1024 + 16 + (size_t)4 * a.N * sizeof(float);
 }
 
-// slab buffers: two when they fit (fill of tile i+1 under the MMAs of tile i); one is accepted only when a tile has >= 4
-// n-tile passes to amortise the exposed fill (on the 3x3 128 -> 128 layer, 2 passes, one buffer measured slower than
-// the TMEM-operand slab kernel: 286 vs 208 us; 1x1 layers with C = 128 and N = 32 / 64 measured 273 / 292 us with one
-// buffer against 230 / 262 us on the gather kernels -- gpurun_out r02j -- so they stay there)
-int direct_nbuf(const ConvArgs &a)
+// Tiling of a layer: {slab buffers, 128-slot sub-tiles per tile}; nbuf = 0: the layer does not fit.
+//  * two slab buffers and 256-slot tiles when they fit (fill of tile i+1 under the MMAs of tile i, weight stages shared by two
+//    sub-tiles);
+//  * 1x1 layers whose two buffers only fit with 128-row tiles take those: they are memory-bound, and with ONE buffer the fill
+//    of the next A tile (128 KB for C = 128) cannot start before the last pass of the current one -- measured on the
+//    128 -> 512 expand layers of ResNet101: fill ~13 us + 8 passes ~14 us per tile, nothing overlapped;
+//  * one buffer is accepted only when a tile has >= 4 n-tile passes to amortise the exposed fill (on the 3x3 128 -> 128
+//    layer, 2 passes, one buffer measured slower than the TMEM-operand slab kernel: 286 vs 208 us; 1x1 layers with C = 128
+//    and N = 32 / 64 measured 273 / 292 us with one buffer against 230 / 262 us on the gather kernels -- gpurun_out r02j).
+struct DirectPlan { int nbuf, dt; };
+DirectPlan direct_plan(const ConvArgs &a)
 {
-    if (direct_smem(a, 2) <= (size_t)D_SMEM_MAX) return 2;
-    if (direct_smem(a, 1) <= (size_t)D_SMEM_MAX && a.N / DBN >= 4) return 1;
-    return 0;
+    const char *e = getenv("ISS_B200_DIRECT_DT1");                       // A/B runs: 0 = never use 128-row tiles
+    const bool dt1 = !(e && e[0] == '0');
+    if (direct_smem(a, 2, 2) <= (size_t)D_SMEM_MAX) return {2, 2};
+    if (dt1 && a.KH * a.KW == 1 && !a.first && a.pool_h == 0 && a.N / DBN >= 4 && direct_smem(a, 2, 1) <= (size_t)D_SMEM_MAX) return {2, 1};
+    if (direct_smem(a, 1, 2) <= (size_t)D_SMEM_MAX && a.N / DBN >= 4) return {1, 2};
+    return {0, 0};
 }
 
 // ---- tensor maps for the TMA mode of the residual layers -------------------------------------------------------------
@@ -707,14 +721,14 @@ bool make_rows_map(CUtensorMap *m, const void *base, int64_t rows, int n)
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int MODE, int NBUF>
+template <int MODE, int NBUF, int DT>
 int launch_tc4h(const ConvArgs &a, const FirstFuse &ff, DirectArgs d, unsigned grid, cudaStream_t st)
 {
-    auto kern = conv_gemm_tc4h_kernel<MODE, NBUF>;
+    auto kern = conv_gemm_tc4h_kernel<MODE, NBUF, DT>;
     ISS_CUDA_OK(iss_optin_smem(reinterpret_cast<const void *>(kern), D_SMEM_MAX));
     DirectMaps maps;
     memset(&maps, 0, sizeof(maps));
-    size_t smem = direct_smem(a, NBUF);
+    size_t smem = direct_smem(a, NBUF, DT);
     if (d.tma) {
         // the ring takes what is left of the shared memory: at least 2 boxes, else the mode is off for this layer
         const int fit = (int)(((size_t)D_SMEM_MAX - smem) / D_RES_BOX);
@@ -749,18 +763,19 @@ bool iss_conv_f16_direct_covers(const ConvArgs &a)
     const int64_t n_img = a.M / ((int64_t)a.OH * a.OW);
     if (n_img * a.H * a.W >= (1ll << 31) - 4096) return false;
     // the IN_FIRST table covers D_TAB images per slab
-    if (a.first && (direct_npix(a) - 1) / (a.H * a.W) + 2 > D_TAB) return false;
-    return direct_nbuf(a) > 0;
+    if (a.first && (direct_npix(a, 2) - 1) / (a.H * a.W) + 2 > D_TAB) return false;
+    return direct_plan(a).nbuf > 0;
 }
 
 // Returns 1 when the layer is not covered (caller continues with the other fp16-split kernels).
 int iss_launch_conv_tc_f16d(ConvArgs &a, cudaStream_t st)
 {
     if (!iss_conv_f16_direct_covers(a)) return 1;
+    const DirectPlan plan = direct_plan(a);
     DirectArgs d = {};
     d.wt = reinterpret_cast<const unsigned char *>(a.wt_f16);
     d.inv_scale = a.wt_f16_inv_scale;
-    d.npix = direct_npix(a);
+    d.npix = direct_npix(a, plan.dt);
     d.n_img = (int)(a.M / ((int64_t)a.OH * a.OW));
     d.total_pix = (int64_t)d.n_img * a.H * a.W;
     d.cb = direct_cb(a);
@@ -771,24 +786,26 @@ int iss_launch_conv_tc_f16d(ConvArgs &a, cudaStream_t st)
     d.n_epi = nepi_env ? (atoi(nepi_env) == 8 ? 8 : 4) : ((a.flags & ISS_F_RESIDUAL) ? 8 : 4);
     // TMA mode of the residual 1x1 layers (ISS_B200_TMA_EPI: 0 off, 1 residual boxes by TMA, 3 + outputs by TMA store)
     {
-        const char *te = getenv("ISS_B200_TMA_EPI");
-        const int want = te ? atoi(te) & 3 : 0;
+        const char *te = getenv("ISS_B200_TMA_EPI");                     // default 1 (+3.2 % on ResNet101, r02o / r02p; 3 measured -0.7 %)
+        const int want = te ? atoi(te) & 3 : 1;
         const bool ok = (a.flags & ISS_F_RESIDUAL) && a.KH * a.KW == 1 && a.N % 32 == 0 && d.n_epi == 8 && !a.first && a.pool_h == 0;
         d.tma = ok ? ((want & 1) ? want : 0) : 0;
     }
     const int64_t total_slots = ((int64_t)(d.n_img - 1) * a.H + a.OH - 1) * a.W + a.OW;
-    d.n_tiles = (int)((total_slots + DT * 128 - 1) / (DT * 128));
+    d.n_tiles = (int)((total_slots + plan.dt * 128 - 1) / (plan.dt * 128));
     int dev = 0, sms = 0;
     ISS_CUDA_OK(cudaGetDevice(&dev));
     ISS_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const unsigned grid = (unsigned)(d.n_tiles < sms ? d.n_tiles : sms);
-    const bool two = direct_nbuf(a) == 2;
+    const bool two = plan.nbuf == 2;
     FirstFuse ff = {};
     if (a.first) {
         ff = *a.first;
-        return two ? launch_tc4h<DIN_FIRST, 2>(a, ff, d, grid, st) : launch_tc4h<DIN_FIRST, 1>(a, ff, d, grid, st);
+        return two ? launch_tc4h<DIN_FIRST, 2, 2>(a, ff, d, grid, st) : launch_tc4h<DIN_FIRST, 1, 2>(a, ff, d, grid, st);
     }
-    if (a.pool_h > 0) return two ? launch_tc4h<DIN_POOL, 2>(a, ff, d, grid, st) : launch_tc4h<DIN_POOL, 1>(a, ff, d, grid, st);
-    if (!a.in_packed) return two ? launch_tc4h<DIN_F32, 2>(a, ff, d, grid, st) : launch_tc4h<DIN_F32, 1>(a, ff, d, grid, st);
-    return two ? launch_tc4h<DIN_PACKED, 2>(a, ff, d, grid, st) : launch_tc4h<DIN_PACKED, 1>(a, ff, d, grid, st);
+    if (a.pool_h > 0) return two ? launch_tc4h<DIN_POOL, 2, 2>(a, ff, d, grid, st) : launch_tc4h<DIN_POOL, 1, 2>(a, ff, d, grid, st);
+    if (plan.dt == 1)                                                    // (128-row tiles: 1x1 layers only, always two buffers)
+        return a.in_packed ? launch_tc4h<DIN_PACKED, 2, 1>(a, ff, d, grid, st) : launch_tc4h<DIN_F32, 2, 1>(a, ff, d, grid, st);
+    if (!a.in_packed) return two ? launch_tc4h<DIN_F32, 2, 2>(a, ff, d, grid, st) : launch_tc4h<DIN_F32, 1, 2>(a, ff, d, grid, st);
+    return two ? launch_tc4h<DIN_PACKED, 2, 2>(a, ff, d, grid, st) : launch_tc4h<DIN_PACKED, 1, 2>(a, ff, d, grid, st);
 }
