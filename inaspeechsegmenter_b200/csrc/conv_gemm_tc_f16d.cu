@@ -153,8 +153,8 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d, 
             mbar_init(&sm->acc_full[b], 1); mbar_init(&sm->acc_empty[b], d.n_epi);
         }
         for (int s = 0; s < DSB; ++s) { mbar_init(&sm->b_full[s], 1); mbar_init(&sm->b_empty[s], 1); }
-        // a box is released by the 4 warps that read it, or (outputs by TMA store) by the one thread that stored it
-        for (int s = 0; s < D_RES_MAX; ++s) { mbar_init(&sm->res_full[s], 1); mbar_init(&sm->res_empty[s], (d.tma & 2) ? 1 : 4); }
+        // a box is released by the 4 warps that read it (outputs by TMA store: once their own rows have left)
+        for (int s = 0; s < D_RES_MAX; ++s) { mbar_init(&sm->res_full[s], 1); mbar_init(&sm->res_empty[s], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -372,13 +372,16 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d, 
                                         sts128(rowa + (((uint32_t)(2 * j) ^ x7) << 4), w.v[0], w.v[1], w.v[2], w.v[3]);
                                         sts128(rowa + (((uint32_t)(2 * j + 1) ^ x7) << 4), w.v[4], w.v[5], w.v[6], w.v[7]);
                                     }
+                                    // every warp stores its own 32 rows of the box (a 32 x 32-word sub-box whose 4 KB start on a
+                                    // 1024-byte boundary, so the swizzle pattern is the box's own): no barrier across the four warps
                                     fence_proxy_async();             // generic-proxy stores -> visible to the TMA store
-                                    asm volatile("bar.sync %0, 128;" ::"r"(2 + egrp) : "memory");        // the 4 warps that share this box
-                                    if ((warp & 3) == 2 && lane == 0) {   // (warps 2 and 6 are the first of their groups)
-                                        if (row0 < a.M) {            // rows behind the last one are clipped by the TMA unit
-                                            tma_store_2d(&maps.out, res_u32 + sl * (uint32_t)D_RES_BOX, nb + c, (int)row0);
+                                    __syncwarp();
+                                    if (lane == 0) {
+                                        const int64_t rq = row0 + quad * 32;
+                                        if (rq < a.M) {              // rows behind the last one are clipped by the TMA unit
+                                            tma_store_2d(&maps.out, res_u32 + sl * (uint32_t)D_RES_BOX + (uint32_t)quad * 4096u, nb + c, (int)rq);
                                             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                                            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the box has been read: it may be refilled
+                                            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the rows have been read: the box may be refilled
                                         }
                                         mbar_arrive(&sm->res_empty[sl]);
                                     }
@@ -710,13 +713,13 @@ EncodeTiledFn encode_tiled()
 }
 // [rows][n] 32-bit words, box = 32 words (128 bytes, SWIZZLE_128B) x 128 rows; elements behind the last row read as zero and
 // are not written
-bool make_rows_map(CUtensorMap *m, const void *base, int64_t rows, int n)
+bool make_rows_map(CUtensorMap *m, const void *base, int64_t rows, int n, int box_rows = 128)
 {
     const EncodeTiledFn enc = encode_tiled();
     if (!enc || (reinterpret_cast<uintptr_t>(base) & 15) != 0 || n % 32 != 0) return false;
     const cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)n * 4};
-    const cuuint32_t box[2] = {32, 128}, estr[2] = {1, 1};
+    const cuuint32_t box[2] = {32, (cuuint32_t)box_rows}, estr[2] = {1, 1};
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -733,7 +736,7 @@ int launch_tc4h(const ConvArgs &a, const FirstFuse &ff, DirectArgs d, unsigned g
         // the ring takes what is left of the shared memory: at least 2 boxes, else the mode is off for this layer
         const int fit = (int)(((size_t)D_SMEM_MAX - smem) / D_RES_BOX);
         d.rs = fit < D_RES_MAX ? fit : D_RES_MAX;
-        if (d.rs < 2 || !make_rows_map(&maps.res, a.residual, a.M, a.N) || ((d.tma & 2) && !make_rows_map(&maps.out, a.out, a.M, a.N))) { d.tma = 0; d.rs = 0; }
+        if (d.rs < 2 || !make_rows_map(&maps.res, a.residual, a.M, a.N) || ((d.tma & 2) && !make_rows_map(&maps.out, a.out, a.M, a.N, 32))) { d.tma = 0; d.rs = 0; }
         else smem += (size_t)d.rs * D_RES_BOX;
     }
     kern<<<grid, D_THREADS, smem, st>>>(a, ff, d, maps);
