@@ -6,7 +6,7 @@ TAG=${1:-ab3}
 mkdir -p gpurun_out
 {
   for i in 1 2; do
-    for cfg in "0 0" "0 1" "1 0" "1 1" "1 3"; do
+    for cfg in "0 0" "0 1" "1 0" "1 1" "1 3"; do        # (defaults: DIRECT_DT1=1 TMA_EPI=1)
       set -- $cfg
       echo "== resnet DIRECT_DT1=$1 TMA_EPI=$2 (#$i)"; ISS_B200_DIRECT_DT1=$1 ISS_B200_TMA_EPI=$2 timeout 150 python tests/tools/resnet_check.py 3 2>&1 | grep -E "^mode 3|rror|Trace|timed out|libiss" | head -5
     done
