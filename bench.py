@@ -729,7 +729,7 @@ def kernel_source_hash():
 
 def ncu_dram_bytes(path):
     """dram__bytes_read.sum + dram__bytes_write.sum (bytes per launch) of the first kernel in a committed
-    `ncu --set full` summary of the same 2048-patch launch (a profiler cannot run inside the timed process).
+    `ncu --set full` summary of the same 8192-patch launch (a profiler cannot run inside the timed process).
     The summary is stamped with the hash of the kernel sources it was captured from: if they changed since,
     the figure is withheld (None, 'stale ...') instead of silently going out of date."""
     if not path or not os.path.exists(path):
