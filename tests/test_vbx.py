@@ -123,6 +123,32 @@ def test_k5_resnet_vs_oracle(vctx, golden):
 
 
 @gpu
+def test_k5_residual_layer_modes_are_bit_identical(vctx, monkeypatch):
+    """The residual 1x1 layers of ResNet101 on the direct kernel: 128-row tiles (ISS_B200_DIRECT_DT1) and the tensor-map
+    TMA modes (ISS_B200_TMA_EPI: residual boxes by cp.async.bulk.tensor, 3 = outputs by TMA store as well) reorder memory
+    traffic only -- every configuration must give the x-vectors of the plain configuration bit for bit, on a window
+    count that leaves a partial tile at the end of every stage."""
+    from inaspeechsegmenter_b200 import vbx_segmenter as vb
+    from oracle import vbx_oracle as vx
+    ext = vb.B200BackendExtractor(state_dict=vx.synthetic_resnet101_state(seed=5), ctx=vctx)
+    g = torch.Generator(device='cpu').manual_seed(3)
+    fea = torch.randn(24 * 37 + 144, 64, generator=g).cuda()
+    starts = np.arange(37) * 24
+    out = {}
+    for dt1, tma in (('0', '0'), ('0', '1'), ('1', '0'), ('1', '1'), ('1', '3'), ('0', '3')):
+        monkeypatch.setenv('ISS_B200_DIRECT_DT1', dt1)
+        monkeypatch.setenv('ISS_B200_TMA_EPI', tma)
+        out[dt1, tma] = ext.embed_windows(fea, starts, 144).cpu().numpy()
+    monkeypatch.delenv('ISS_B200_DIRECT_DT1')
+    monkeypatch.delenv('ISS_B200_TMA_EPI')
+    out['default'] = ext.embed_windows(fea, starts, 144).cpu().numpy()
+    ref = out['0', '0']
+    assert np.isfinite(ref).all() and np.abs(ref).max() > 0
+    for k, v in out.items():
+        assert np.array_equal(v, ref), k
+
+
+@gpu
 def test_vbx_extractor_call_vs_oracle(vctx, golden):
     """B200BackendExtractor.__call__ (batched) == the reference windowing loop with the oracle network."""
     from inaspeechsegmenter_b200 import vbx_segmenter as vb
