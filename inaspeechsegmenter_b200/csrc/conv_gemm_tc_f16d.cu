@@ -58,7 +58,7 @@ constexpr int D_B_STAGE = 2 * DBN * 128;                // [hi rows | lo rows]
 constexpr int D_TAB = 8;                                // images a slab may touch (IN_FIRST table)
 constexpr int D_SMEM_MAX = 232448;
 
-constexpr int DIN_PACKED = 1, DIN_FIRST = 2, DIN_POOL = 3, DIN_F32 = 4;
+constexpr int DIN_PACKED = 1, DIN_FIRST = 2, DIN_POOL = 3, DIN_F32 = 4, DIN_PAD = 5;
 constexpr int D_RES_BOX = 128 * 128;                    // one residual / output box: 128 rows x 32 channels (128 B, SWIZZLE_128B)
 constexpr int D_RES_MAX = 4;                            // boxes in the ring at most
 
@@ -607,10 +607,15 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d, 
                 // task = (pixel pl, chunk jj of 8 channels): two 16-byte loads (split-half words, or fp32 values split here)
                 // -> one 16-byte chunk of the hi plane and one of the lo plane of channel block jj >> 3; chunks past the
                 // real channel count (C = 32 padded to 64) are zero
+                // DIN_PAD ('same' 3x3, padding 1): the tall image is the PADDED one -- a.H = H + 1 rows of a.W = W + 1 pixels per
+                // image, row 0 and column 0 zero; the zero column of the next row / zero row of the next image serve as this
+                // row's right / this image's bottom padding, so the tap windows stay plain row shifts -- and pixel (r, cc) of it
+                // is pixel (r - 1, cc - 1) of the un-padded NHWC input
                 const uint4 *src = reinterpret_cast<const uint4 *>(a.in);
                 const int cshift = 3 + (d.cb == 1 ? 0 : d.cb == 2 ? 1 : 2), cpp = 1 << cshift;      // chunks per pixel
                 const int creal = d.c_real >> 3, q4 = d.c_real >> 2;                                // real chunks / uint4 per pixel
                 const int total = d.npix << cshift;
+                const int64_t Hr = a.H - 1, Wr = a.W - 1;               // (DIN_PAD) the un-padded input
                 constexpr int FB = 4;                                   // tasks whose loads are in flight together
                 for (int idx0 = ftid; idx0 < total; idx0 += FB * nfill) {
                     u32x8 u[FB];
@@ -621,8 +626,17 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d, 
                         for (int e = 0; e < 8; ++e) u[f].v[e] = 0u;
                         if (idx < total) {
                             const int pl = idx >> cshift, jj = idx & (cpp - 1);
-                            const int64_t gp = (int64_t)s0 + pl;
-                            if (gp < d.total_pix && jj < creal) u[f] = ldg256(src + gp * q4 + jj * 2);
+                            int64_t gp = (int64_t)s0 + pl;
+                            bool live = gp < d.total_pix && jj < creal;
+                            if constexpr (MODE == DIN_PAD) {
+                                if (live) {
+                                    const uint32_t img = (uint32_t)gp / HW, rem = (uint32_t)gp - img * HW;
+                                    const uint32_t r = rem / (uint32_t)a.W, cc = rem - r * (uint32_t)a.W;
+                                    live = r >= 1u && cc >= 1u;
+                                    gp = ((int64_t)img * Hr + (int64_t)r - 1) * Wr + (int64_t)cc - 1;
+                                }
+                            }
+                            if (live) u[f] = ldg256(src + gp * q4 + jj * 2);
                         }
                     }
 #pragma unroll
@@ -696,6 +710,32 @@ DirectPlan direct_plan(const ConvArgs &a)
     return {0, 0};
 }
 
+// 'same' 3x3 / stride-1 convolution with padding 1 (ResNet101's 3x3 layers, Keras padding='same'): runs as the un-padded
+// convolution of the padded tall image (H + 1 rows of W + 1 pixels per image, see the DIN_PAD fill) -- 92 % useful slots
+// on the 16 x 36 maps of ResNet101's stage 3, where the gather kernel spends its time on im2col copies.
+// ISS_B200_DIRECT_PAD=0 turns it off (A/B runs).
+bool direct_is_same3x3(const ConvArgs &a)
+{
+    const char *e = getenv("ISS_B200_DIRECT_PAD");
+    if (e && e[0] == '0') return false;
+    return a.KH == 3 && a.KW == 3 && a.SH == 1 && a.SW == 1 && a.PT == 1 && a.PL == 1 && a.OH == a.H && a.OW == a.W && a.in_packed && !a.first &&
+           a.pool_h == 0 && !(a.flags & ISS_F_RESIDUAL);
+}
+ConvArgs direct_padded_view(const ConvArgs &a)
+{
+    ConvArgs b = a;
+    b.H = a.H + 1; b.W = a.W + 1; b.PT = 0; b.PL = 0;                    // OH / OW stay the real output dims
+    return b;
+}
+// (one slab buffer, two n-tile passes: accepted for the padded 3x3 layers -- on ResNet101's 128 -> 128 layers the exposed
+//  fill costs less than the gather kernel's producers)
+DirectPlan direct_plan_padded(const ConvArgs &b)
+{
+    if (direct_smem(b, 2, 2) <= (size_t)D_SMEM_MAX) return {2, 2};
+    if (direct_smem(b, 1, 2) <= (size_t)D_SMEM_MAX && b.N / DBN >= 2) return {1, 2};
+    return {0, 0};
+}
+
 // ---- tensor maps for the TMA mode of the residual layers -------------------------------------------------------------
 // cuTensorMapEncodeTiled is a driver entry point: fetched through the runtime so that the library does not link libcuda
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -755,6 +795,14 @@ bool iss_conv_f16_direct_covers(const ConvArgs &a)
 {
     const char *env = getenv("ISS_B200_F16_DIRECT");                     // read per call: the GPU tests toggle it
     if (env && env[0] == '0') return false;
+    if (a.wt_f16 && direct_is_same3x3(a)) {
+        const ConvArgs b = direct_padded_view(a);
+        const bool c_ok = a.C == 64 || a.C == 128 || a.C == 256;
+        if (!c_ok || a.N % DBN != 0 || a.N > D_NMAX || a.K != 9 * a.C || a.Kp != a.K || (a.flags & ISS_F_SIGMOID)) return false;
+        const int64_t n_img = a.M / ((int64_t)a.OH * a.OW);
+        if (n_img * b.H * b.W >= (1ll << 31) - 4096) return false;
+        return direct_plan_padded(b).nbuf > 0;
+    }
     if (!a.wt_f16 || a.SH != 1 || a.SW != 1 || a.PT != 0 || a.PL != 0) return false;
     if (a.OH != a.H - a.KH + 1 || a.OW != a.W - a.KW + 1 || a.Kp != a.K) return false;
     const bool c_ok = a.C == 64 || a.C == 128 || a.C == 256 || (a.C == 32 && a.KH * a.KW == 1);
@@ -771,10 +819,12 @@ bool iss_conv_f16_direct_covers(const ConvArgs &a)
 }
 
 // Returns 1 when the layer is not covered (caller continues with the other fp16-split kernels).
-int iss_launch_conv_tc_f16d(ConvArgs &a, cudaStream_t st)
+int iss_launch_conv_tc_f16d(ConvArgs &a_in, cudaStream_t st)
 {
-    if (!iss_conv_f16_direct_covers(a)) return 1;
-    const DirectPlan plan = direct_plan(a);
+    if (!iss_conv_f16_direct_covers(a_in)) return 1;
+    const bool pad = direct_is_same3x3(a_in);
+    ConvArgs a = pad ? direct_padded_view(a_in) : a_in;                  // (padded: the kernel sees the un-padded convolution of the padded image)
+    const DirectPlan plan = pad ? direct_plan_padded(a) : direct_plan(a);
     DirectArgs d = {};
     d.wt = reinterpret_cast<const unsigned char *>(a.wt_f16);
     d.inv_scale = a.wt_f16_inv_scale;
@@ -807,6 +857,7 @@ int iss_launch_conv_tc_f16d(ConvArgs &a, cudaStream_t st)
         return two ? launch_tc4h<DIN_FIRST, 2, 2>(a, ff, d, grid, st) : launch_tc4h<DIN_FIRST, 1, 2>(a, ff, d, grid, st);
     }
     if (a.pool_h > 0) return two ? launch_tc4h<DIN_POOL, 2, 2>(a, ff, d, grid, st) : launch_tc4h<DIN_POOL, 1, 2>(a, ff, d, grid, st);
+    if (pad) return two ? launch_tc4h<DIN_PAD, 2, 2>(a, ff, d, grid, st) : launch_tc4h<DIN_PAD, 1, 2>(a, ff, d, grid, st);
     if (plan.dt == 1)                                                    // (128-row tiles: 1x1 layers only, always two buffers)
         return a.in_packed ? launch_tc4h<DIN_PACKED, 2, 1>(a, ff, d, grid, st) : launch_tc4h<DIN_F32, 2, 1>(a, ff, d, grid, st);
     if (!a.in_packed) return two ? launch_tc4h<DIN_F32, 2, 2>(a, ff, d, grid, st) : launch_tc4h<DIN_F32, 1, 2>(a, ff, d, grid, st);

@@ -74,3 +74,71 @@ def test_direct_addressing_is_a_valid_convolution(n, H, W, KH, KW):
 def test_useful_row_fraction_of_the_segmenter_layer():
     H, W, KH, KW = 65, 17, 5, 4
     assert abs(((H - KH + 1) / H) * ((W - KW + 1) / W) - 0.773) < 1e-3
+
+
+def direct_conv_same3x3(x, w):
+    """'same' 3x3 / stride-1 / padding-1 convolution through the kernel's DIN_PAD addressing: the tall image is the padded
+    one (H + 1 rows of W + 1 pixels per image, row 0 and column 0 zero; the next row's zero column and the next image's
+    zero row are this row's right and this image's bottom padding), the tap windows stay plain row shifts, slot
+    s = (img * (H + 1) + oh) * (W + 1) + ow is a real output iff oh < H and ow < W."""
+    n, H, W, C = x.shape
+    N = w.shape[3]
+    assert C == HBK and w.shape[:2] == (3, 3)
+    Hp, Wp = H + 1, W + 1
+    npix = (DT * 128 + 2 * Wp + 2 + 7) & ~7
+    total_pix = n * Hp * Wp
+    total_slots = ((n - 1) * Hp + H - 1) * Wp + W
+    n_tiles = (total_slots + DT * 128 - 1) // (DT * 128)
+    flat = x.reshape(n * H * W, C)
+    y = np.full((n, H, W, N), np.nan)
+    wk = w.reshape(9, C, N)
+    for tile in range(n_tiles):
+        s0 = tile * DT * 128
+        slab = np.zeros((npix, 8, 8))
+        for pl in range(npix):                                # the DIN_PAD fill
+            gp = s0 + pl
+            row = np.zeros(C)
+            if gp < total_pix:
+                img, rem = divmod(gp, Hp * Wp)
+                r, cc = divmod(rem, Wp)
+                if r >= 1 and cc >= 1:
+                    row = flat[(img * H + r - 1) * W + cc - 1]
+            for j in range(8):
+                slab[pl, j ^ (pl & 7)] = row[8 * j:8 * j + 8]
+        for t in range(DT):
+            acc = np.zeros((128, N))
+            for kb in range(9):
+                kh, kw = divmod(kb, 3)
+                first = t * 128 + kh * Wp + kw
+                assert first + 128 <= npix, 'window leaves the slab'
+                a = np.empty((128, C))
+                for m in range(128):
+                    r = first + m
+                    for j in range(8):
+                        a[m, 8 * j:8 * j + 8] = slab[r, j ^ (r & 7)]
+                acc += a @ wk[kb]
+            for m in range(128):
+                slot = s0 + t * 128 + m
+                img, rem = divmod(slot, Hp * Wp)
+                oh, ow = divmod(rem, Wp)
+                if img < n and oh < H and ow < W:
+                    assert np.isnan(y[img, oh, ow, 0]), 'slot written twice'
+                    y[img, oh, ow] = acc[m]
+    return y
+
+
+@pytest.mark.parametrize('n,H,W', [(3, 16, 36), (5, 8, 18), (2, 5, 3), (1, 1, 1), (4, 7, 40)])
+def test_padded_direct_addressing_is_a_same_convolution(n, H, W):
+    rng = np.random.default_rng(n * 100 + H)
+    x = rng.standard_normal((n, H, W, HBK))
+    w = rng.standard_normal((3, 3, HBK, 8))
+    y = direct_conv_same3x3(x, w)
+    assert not np.isnan(y).any(), 'an output was never produced'
+    xp = np.zeros((n, H + 2, W + 2, HBK))
+    xp[:, 1:-1, 1:-1] = x
+    ref = np.zeros((n, H, W, 8))
+    for kh in range(3):
+        for kw in range(3):
+            ref += np.einsum('nhwc,co->nhwo', xp[:, kh:kh + H, kw:kw + W], w[kh, kw])
+    np.testing.assert_allclose(y, ref, rtol=1e-12, atol=1e-12)
+    assert abs((16 / 17) * (36 / 37) - 0.916) < 1e-3          # useful slots on ResNet101's stage-3 maps
