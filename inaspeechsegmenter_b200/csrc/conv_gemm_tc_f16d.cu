@@ -76,6 +76,7 @@ struct DirectArgs {
     int n_epi;                  // epilogue warps: 4 (one per TMEM lane quadrant, both sub-tiles) or 8 (one per quadrant and sub-tile)
     int tma;                    // residual 1x1 layers: bit 0 = residual boxes by tensor-map TMA (cp.async.bulk.tensor), bit 1 = outputs by TMA store
     int rs;                     // boxes in the residual ring (2 .. D_RES_MAX)
+    int dbg;                    // diagnostics (ISS_B200_TMA_DBG): 1 = release a box after the stores, 2 = no L2 prefetch cursor
 };
 // tensor maps of the residual and the output tensor ([M rows][N words], box 32 words x 128 rows, SWIZZLE_128B); zero when unused
 struct alignas(64) DirectMaps { CUtensorMap res, out; };
@@ -359,12 +360,12 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d, 
                                     lds128(rowa + (((uint32_t)(2 * j + 1) ^ x7) << 4), rw[j].v[4], rw[j].v[5], rw[j].v[6], rw[j].v[7]);
                                 }
                                 if (!tma_st) {
-                                    __syncwarp();
-                                    if (lane == 0) mbar_arrive(&sm->res_empty[sl]);          // 4 warps read a box
+                                    if (!(d.dbg & 1)) { __syncwarp(); if (lane == 0) mbar_arrive(&sm->res_empty[sl]); }          // 4 warps read a box
                                     if (valid) {
 #pragma unroll
                                         for (int j = 0; j < 4; ++j) stg256(dst + c + 8 * j, finish8(acc + 8 * j, rw[j], nb + c + 8 * j));
                                     }
+                                    if (d.dbg & 1) { __syncwarp(); if (lane == 0) mbar_arrive(&sm->res_empty[sl]); }             // (diagnostic: late release)
                                 } else {
 #pragma unroll
                                     for (int j = 0; j < 4; ++j) {
@@ -444,7 +445,7 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d, 
             __syncwarp();
             pf_more = advance(pf);
         };
-        for (int i = 0; i < D_RES_AHEAD; ++i) prefetch();
+        if (!(d.dbg & 2)) for (int i = 0; i < D_RES_AHEAD; ++i) prefetch();
         for (uint32_t g = 0; more; ++g) {
             const uint32_t sl = g % (uint32_t)d.rs, use = g / (uint32_t)d.rs;
             int c0, r0;
@@ -456,7 +457,7 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d, 
                 tma_load_2d(res_u32 + sl * (uint32_t)D_RES_BOX, &maps.res, c0, r0, bar);
             }
             __syncwarp();
-            prefetch();
+            if (!(d.dbg & 2)) prefetch();
             more = advance(cur);
         }
     } else {
@@ -843,6 +844,8 @@ int iss_launch_conv_tc_f16d(ConvArgs &a_in, cudaStream_t st)
         const int want = te ? atoi(te) & 3 : 1;
         const bool ok = (a.flags & ISS_F_RESIDUAL) && a.KH * a.KW == 1 && a.N % 32 == 0 && d.n_epi == 8 && !a.first && a.pool_h == 0;
         d.tma = ok ? ((want & 1) ? want : 0) : 0;
+        const char *dbg = getenv("ISS_B200_TMA_DBG");
+        d.dbg = dbg ? atoi(dbg) : 0;
     }
     const int64_t total_slots = ((int64_t)(d.n_img - 1) * a.H + a.OH - 1) * a.W + a.OW;
     d.n_tiles = (int)((total_slots + plan.dt * 128 - 1) / (plan.dt * 128));
