@@ -476,7 +476,7 @@ def config3_block(torch, args, dev, peaks):
     file_sec = 3600
     nfiles = max(1, int(round(args.vbx_hours)))
 
-    def one_file(src):
+    def one_file(src, keep=None):
         """get_features + VBxExtractor.__call__ windows (vbx_segmenter.py:72-89,217-246) of one 1 h file -> embeddings on the host."""
         pcm = src if src.is_cuda else src.to(dev, non_blocking=True)
         fea = fe(pcm)
@@ -487,6 +487,8 @@ def config3_block(torch, args, dev, peaks):
         for s, nn, tail in plan:
             if tail:
                 ext.embed_windows(fea, [s], nn).cpu()
+        if keep is not None:
+            keep['fea'], keep['reg'], keep['emb'] = fea, reg, out
         return len(plan), out
 
     blocks = [synth_range(torch, f * file_sec * SR, (f + 1) * file_sec * SR, dev) for f in range(min(nfiles, 2))]
@@ -520,12 +522,34 @@ def config3_block(torch, args, dev, peaks):
     # CPU: the reference's torch backend (resnet.py, vbx_segmenter.py:271-288) restated, all host cores, a bounded sample of windows
     torch.set_num_threads(host_cores())
     net = vx.ResNet101Oracle(sd)
+    # the 32 CPU windows are REAL windows of the benchmark file, spread over all of its sweeps: their x-vectors double as the
+    # benchmark-scale parity check of K5 (the GPU embeddings of the same windows come out of full 256-window sweeps)
+    keep = {}
+    k5_parity = None
     xw = torch.randn(32, 64, 144)
+    pick = list(range(32))
+    try:
+        one_file(blocks[0], keep)
+        reg = keep['reg']
+        pick = sorted(set(int(i) for i in np.linspace(0, len(reg) - 1, 32)))
+        xw = torch.stack([keep['fea'][reg[i]:reg[i] + vb.WINLEN].T.contiguous() for i in pick]).cpu()
+    except Exception as e:                                               # (the timing below must survive a parity-plumbing error)
+        k5_parity = {'error': repr(e)}
     net.forward(xw[:4])
     tc0 = time.perf_counter()
-    net.forward(xw)
+    yw = net.forward(xw)
     tcpu = time.perf_counter() - tc0
-    cpu_win_s = 32 / tcpu
+    cpu_win_s = len(pick) / tcpu
+    if k5_parity is None:
+        try:
+            yw = np.asarray(yw.detach().cpu().numpy() if hasattr(yw, 'detach') else yw, dtype=np.float32).reshape(len(pick), -1)
+            got = keep['emb'].numpy()[pick]
+            k5_rel = float(np.abs(got - yw).max() / max(np.abs(yw).max(), 1e-30))
+            k5_parity = {'windows': len(pick), 'max_rel_err': k5_rel, 'tolerance': 2e-4, 'ok': bool(k5_rel <= 2e-4),
+                         'oracle': 'oracle/vbx_oracle.py ResNet101Oracle (bit-identical to the real resnet.py on seeded weights)'}
+        except Exception as e:
+            k5_parity = {'error': repr(e)}
+    del keep
     win_per_hour = nwin / hours
     return {
         'workload': 'VBx x-vector path (features_vbx + resnet.py ResNet101) on %g h synthetic 16 kHz mono as 1 h files, 1xB200 (BASELINE configs[3] = 50 h)' % hours
@@ -539,7 +563,8 @@ def config3_block(torch, args, dev, peaks):
                         'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)' if 'bf16_tflops_sustained' in peaks else 'fallback 1.4 PFLOP/s (of fallback)',
                         'note': 'whole x-vector path time (features 0.2 %, ResNet 99 %)'},
         'cpu_baseline': {'value': cpu_win_s / win_per_hour, 'unit': UNIT, 'cores': host_cores(), 'kind': 'port',
-                         'sample': '32 windows of 144 frames through the torch-CPU restatement of resnet.py (the reference\'s own torch backend, vbx_segmenter.py:271-288), all host cores; %.1f windows/s' % cpu_win_s},
+                         'sample': '32 windows of 144 frames of the benchmark file through the torch-CPU restatement of resnet.py (the reference\'s own torch backend, vbx_segmenter.py:271-288), all host cores; %.1f windows/s' % cpu_win_s},
+        'parity': k5_parity,
         'weights': 'seeded synthetic ResNet101 (final.onnx / raw_81.pth absent)',
     }
 

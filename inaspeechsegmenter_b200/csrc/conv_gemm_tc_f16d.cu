@@ -348,7 +348,10 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d, 
                         if (tma) {
                             const uint32_t ck = chunk + (uint32_t)(c >> 5);
                             {
-                                const uint32_t g = (uint32_t)DT * ck + (uint32_t)t, sl = g % (uint32_t)d.rs, use = g / (uint32_t)d.rs;
+                                // each group of four warps owns one half of the ring: its k-th box sits in slot k % half of that half
+                                // (one consumer per slot: a waiter can never be two phases away from the phase it waits for)
+                                const uint32_t half = (uint32_t)d.rs >> 1, k = DT == 2 ? ck : ck >> 1;
+                                const uint32_t sl = (uint32_t)egrp * half + k % half, use = k / half;
                                 mbar_wait(&sm->res_full[sl], use & 1u, 8);      // every reading thread observes the completion itself
                                 // this lane's row of the box: 128 bytes, 16-byte chunk q at q ^ (row & 7) (SWIZZLE_128B)
                                 const uint32_t r = (uint32_t)(quad * 32 + lane);
@@ -360,7 +363,21 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d, 
                                     lds128(rowa + (((uint32_t)(2 * j + 1) ^ x7) << 4), rw[j].v[4], rw[j].v[5], rw[j].v[6], rw[j].v[7]);
                                 }
                                 if (!tma_st) {
-                                    if (!(d.dbg & 1)) { __syncwarp(); if (lane == 0) mbar_arrive(&sm->res_empty[sl]); }          // 4 warps read a box
+                                    if (!(d.dbg & 1)) {
+                                        // Release the box as soon as its words are IN REGISTERS, not merely requested: an arrive issued
+                                        // right behind the LDS let the producer's refill overtake the reads (measured: r02t / r02u, wrong
+                                        // residuals in most windows -- the loads queue behind the tensor core's operand traffic).  Every
+                                        // loaded word feeds the barrier address, so the arrive cannot issue before the loads have landed.
+                                        uint32_t dep = 0;
+#pragma unroll
+                                        for (int j = 0; j < 4; ++j)
+#pragma unroll
+                                            for (int q = 0; q < 8; ++q) dep ^= rw[j].v[q];
+                                        asm volatile("and.b32 %0, %0, 0;" : "+r"(dep));
+                                        __syncwarp();
+                                        if (lane == 0)
+                                            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&sm->res_empty[sl]) + dep) : "memory");   // 4 warps read a box
+                                    }
                                     if (valid) {
 #pragma unroll
                                         for (int j = 0; j < 4; ++j) stg256(dst + c + 8 * j, finish8(acc + 8 * j, rw[j], nb + c + 8 * j));
@@ -446,8 +463,11 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d, 
             pf_more = advance(pf);
         };
         if (!(d.dbg & 2)) for (int i = 0; i < D_RES_AHEAD; ++i) prefetch();
-        for (uint32_t g = 0; more; ++g) {
-            const uint32_t sl = g % (uint32_t)d.rs, use = g / (uint32_t)d.rs;
+        uint32_t ck = 0;                                              // running (tile, pass, half) count, as in the epilogue
+        while (more) {
+            // the consumers' slot rule: group = sub-tile (DT = 2) or 32-channel half (DT = 1), k = that group's box count
+            const uint32_t half = (uint32_t)d.rs >> 1, grp = DT == 2 ? (uint32_t)cur.t : (uint32_t)(cur.c >> 5), k = DT == 2 ? ck : ck >> 1;
+            const uint32_t sl = grp * half + k % half, use = k / half;
             int c0, r0;
             box_of(cur, c0, r0);
             mbar_wait(&sm->res_empty[sl], (use & 1u) ^ 1u, 7);
@@ -458,6 +478,7 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d, 
             }
             __syncwarp();
             if (!(d.dbg & 2)) prefetch();
+            if (cur.t == DT - 1) ++ck;                                // the last sub-tile of a (tile, pass, half) chunk
             more = advance(cur);
         }
     } else {
@@ -776,7 +797,7 @@ int launch_tc4h(const ConvArgs &a, const FirstFuse &ff, DirectArgs d, unsigned g
     if (d.tma) {
         // the ring takes what is left of the shared memory: at least 2 boxes, else the mode is off for this layer
         const int fit = (int)(((size_t)D_SMEM_MAX - smem) / D_RES_BOX);
-        d.rs = fit < D_RES_MAX ? fit : D_RES_MAX;
+        d.rs = (fit < D_RES_MAX ? fit : D_RES_MAX) & ~1;               // one half per group of four epilogue warps
         if (d.rs < 2 || !make_rows_map(&maps.res, a.residual, a.M, a.N) || ((d.tma & 2) && !make_rows_map(&maps.out, a.out, a.M, a.N, 32))) { d.tma = 0; d.rs = 0; }
         else smem += (size_t)d.rs * D_RES_BOX;
     }

@@ -137,8 +137,8 @@ def test_k5_residual_layer_modes_are_bit_identical(vctx, monkeypatch):
         fea = torch.randn(24 * nwin + 144, 64, generator=g).cuda()
         starts = np.arange(nwin) * 24
         out = {}
-        cfgs = [('0', '0', '0'), ('0', '1', '0'), ('0', '1', '0'), ('0', '1', '0'), ('1', '0', '0'), ('1', '1', '0'), ('1', '1', '1'), ('1', '1', '2'),
-                ('1', '1', '3'), ('1', '3', '0'), ('0', '3', '0'), ('0', '0', '0')]
+        cfgs = [('0', '0', '0'), ('0', '1', '0'), ('0', '1', '0'), ('1', '1', '0'), ('1', '1', '0'), ('1', '1', '0'), ('1', '1', '1'), ('0', '1', '1'),
+                ('1', '0', '0'), ('1', '3', '0'), ('0', '3', '0'), ('1', '1', '2')]
         for n, (dt1, tma, dbg) in enumerate(cfgs):
             monkeypatch.setenv('ISS_B200_DIRECT_DT1', dt1)
             monkeypatch.setenv('ISS_B200_TMA_EPI', tma)
