@@ -132,26 +132,30 @@ def test_k5_residual_layer_modes_are_bit_identical(vctx, monkeypatch):
     from oracle import vbx_oracle as vx
     ext = vb.B200BackendExtractor(state_dict=vx.synthetic_resnet101_state(seed=5), ctx=vctx)
     g = torch.Generator(device='cpu').manual_seed(3)
-    bad, seen = [], []
-    for nwin in (37, 256 + 5, 700):
+    bad = []
+    for nwin in (37, 256 + 5, 700):                                   # partial tiles / one sweep + a remainder / several sweeps
         fea = torch.randn(24 * nwin + 144, 64, generator=g).cuda()
         starts = np.arange(nwin) * 24
         out = {}
-        cfgs = [('0', '0', '0'), ('0', '1', '0'), ('0', '1', '0'), ('1', '1', '0'), ('1', '1', '0'), ('1', '1', '0'), ('1', '1', '1'), ('0', '1', '1'),
-                ('1', '0', '0'), ('1', '3', '0'), ('0', '3', '0'), ('1', '1', '2')]
-        for n, (dt1, tma, dbg) in enumerate(cfgs):
+        for n, (dt1, tma, pad) in enumerate((('0', '0', '0'), ('0', '1', '0'), ('1', '0', '0'), ('1', '1', '0'), ('1', '3', '0'), ('0', '3', '0'),
+                                             ('1', '1', '0'), ('1', '0', '0'))):
             monkeypatch.setenv('ISS_B200_DIRECT_DT1', dt1)
             monkeypatch.setenv('ISS_B200_TMA_EPI', tma)
-            monkeypatch.setenv('ISS_B200_TMA_DBG', dbg)
-            out[n, dt1, tma, dbg] = ext.embed_windows(fea, starts, 144).cpu().numpy()
-        ref = out[0, '0', '0', '0']
+            out[n, dt1, tma] = ext.embed_windows(fea, starts, 144).cpu().numpy()
+        monkeypatch.delenv('ISS_B200_DIRECT_DT1')
+        monkeypatch.delenv('ISS_B200_TMA_EPI')
+        out['default'] = ext.embed_windows(fea, starts, 144).cpu().numpy()
+        ref = out[0, '0', '0']
         assert np.isfinite(ref).all() and np.abs(ref).max() > 0
         for k, v in out.items():
             nbad = int((v != ref).any(axis=1).sum())
-            seen.append((nwin, k, nbad))
             if nbad:
                 bad.append((nwin, k, nbad, float(np.abs(v - ref).max())))
-    print('MODES', seen)
+        # the padded 3x3 layers on the direct kernel use another accumulation order: same x-vectors within the engine's tolerance
+        monkeypatch.setenv('ISS_B200_DIRECT_PAD', '1')
+        v = ext.embed_windows(fea, starts, 144).cpu().numpy()
+        monkeypatch.delenv('ISS_B200_DIRECT_PAD')
+        assert np.abs(v - ref).max() <= 2e-4 * np.abs(ref).max(), (nwin, float(np.abs(v - ref).max()))
     assert not bad, bad
 
 
