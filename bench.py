@@ -742,13 +742,35 @@ def dominant_profile(mode):
     return os.path.join(ROOT, 'profiles', name) if name else None
 
 
+def _strip_cxx_comments(src):
+    """C++ source without comments and without white space: the text the compiler's result depends on."""
+    out, i, n = [], 0, len(src)
+    while i < n:
+        c = src[i]
+        if c == '"' or c == "'":                                          # string / character literal: copied verbatim
+            j = i + 1
+            while j < n and src[j] != c:
+                j += 2 if src[j] == '\\' else 1
+            out.append(src[i:j + 1]); i = j + 1
+        elif src.startswith('//', i):
+            j = src.find('\n', i)
+            i = n if j < 0 else j
+        elif src.startswith('/*', i):
+            j = src.find('*/', i + 2)
+            i = n if j < 0 else j + 2
+        else:
+            out.append(c); i += 1
+    return ''.join(''.join(out).split())
+
+
 def kernel_source_hash():
-    """sha256 over the sources of the dominant kernel; tools/ncu_summary.py stamps it into the profile summary."""
+    """sha256 over the CODE (comments and white space stripped) of the dominant kernel's sources; tools/ncu_summary.py
+    stamps it into the profile summary."""
     import hashlib
     h = hashlib.sha256()
     for f in ('conv_gemm_tc_f16d.cu', 'tc_common.cuh', 'conv_gemm.cuh'):
-        with open(os.path.join(ROOT, 'inaspeechsegmenter_b200', 'csrc', f), 'rb') as fh:
-            h.update(fh.read())
+        with open(os.path.join(ROOT, 'inaspeechsegmenter_b200', 'csrc', f)) as fh:
+            h.update(_strip_cxx_comments(fh.read()).encode())
     return h.hexdigest()
 
 

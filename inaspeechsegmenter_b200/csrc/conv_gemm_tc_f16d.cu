@@ -366,11 +366,16 @@ conv_gemm_tc4h_kernel(const ConvArgs a, const FirstFuse ff, const DirectArgs d, 
 #pragma unroll
                                         for (int j = 0; j < 4; ++j) stg256(dst + c + 8 * j, finish8(acc + 8 * j, rw[j], nb + c + 8 * j));
                                     }
-                                    // The box is released BEHIND the stores.  Releasing it right after the reads -- even with the
-                                    // arrive made data-dependent on every loaded word -- gave wrong residuals in most windows of a
-                                    // 261-window batch (gpurun_out r02t / r02u / r02v: 0 mismatches with this order at 37 / 261 / 700
-                                    // windows and both tilings, hundreds with the early release).  The cause is not understood, which
-                                    // is why the TMA mode is opt-in and the plain LDG epilogue the default.
+                                    // The box is released BEHIND the stores, i.e. after the residual words have been USED.  An arrive
+                                    // issued right behind the LDS (the first form of this mode) gave wrong residuals in most windows
+                                    // of a large batch (gpurun_out r02t / r02u / r02v): the loads are still queued -- the tensor
+                                    // core's operand reads keep the shared memory busy -- when the barrier flips, and the producer's
+                                    // refill (an L2 hit thanks to the prefetch cursor; fewer mismatches without it) lands first.  A
+                                    // variant that XOR-ed every loaded word into the barrier address "& 0" changed nothing because
+                                    // ptxas folds the AND and with it the dependency (checked in the SASS).  This order: 0 mismatches
+                                    // at 37 / 261 / 700 windows, both tilings, every run.  An early release with a dependency the
+                                    // assembler cannot fold is the obvious next experiment; until it has run on hardware the mode
+                                    // stays opt-in and the plain LDG epilogue is the default.
                                     __syncwarp();
                                     if (lane == 0) mbar_arrive(&sm->res_empty[sl]);          // 4 warps read a box
                                 } else {
@@ -853,7 +858,8 @@ int iss_launch_conv_tc_f16d(ConvArgs &a_in, cudaStream_t st)
     // TMA mode of the residual 1x1 layers (ISS_B200_TMA_EPI: 0 off, 1 residual boxes by TMA, 3 + outputs by TMA store)
     {
         // default 0: the mode is validated bit-identical (tests/test_vbx.py) and 1.7 % faster (107.9 vs 106.1 TFLOP/s on ResNet101, r02v),
-        // but an earlier variant of its box hand-over failed for a reason that is not understood -- see the epilogue
+        // but its first form had a write-after-read race on the ring (see the epilogue) that the single-window checks of the time
+        // did not see; it stays opt-in until it has more hardware mileage
         const char *te = getenv("ISS_B200_TMA_EPI");
         const int want = te ? atoi(te) & 3 : 0;
         const bool ok = (a.flags & ISS_F_RESIDUAL) && a.KH * a.KW == 1 && a.N % 32 == 0 && d.n_epi == 8 && !a.first && a.pool_h == 0;
