@@ -225,3 +225,16 @@ sys.stdout.buffer.write(hdr + b'data' + struct.pack('<I', 0xFFFFFFFF) + pcm)
     assert raw16.dtype == np.int16 and len(raw16) == 32000
     with pytest.raises(Exception, match='Invalid data found'):
         iss_io.media2sig16kmono(str(tmp_path / 'broken.wav'), ffmpeg=str(fake))
+
+
+def test_kernel_source_stamp_ignores_comments_only():
+    """bench.py quotes roofline.traffic from a committed ncu summary only when the summary's stamp equals the hash of the
+    kernel's CODE: comments and white space must not change the stamp, code must."""
+    import bench
+    a = 'int f(int x) { return x + 1; }  // adds one\n/* block\n   comment */ const char *s = "a // b /* c */";\n'
+    b = 'int f(int x)\n{\n    return x + 1;\n}\nconst char *s = "a // b /* c */";   // moved\n'
+    c = 'int f(int x) { return x + 2; }\nconst char *s = "a // b /* c */";\n'
+    assert bench._strip_cxx_comments(a) == bench._strip_cxx_comments(b) != bench._strip_cxx_comments(c)
+    assert '"a//b/*c*/"' in bench._strip_cxx_comments(a)                  # comment markers inside a literal are not comments
+    assert 'addsone' not in bench._strip_cxx_comments(a) and 'moved' not in bench._strip_cxx_comments(b)
+    assert len(bench.kernel_source_hash()) == 64
