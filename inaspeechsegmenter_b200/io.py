@@ -10,7 +10,6 @@ Additionally ``return_int16=True`` hands back the raw int16 samples when the
 source is PCM16 so that the device front-end can ingest 2 bytes/sample (the
 conversion s/32768 then happens in the kernel, bit-identical to soundfile's).
 """
-import os
 import struct
 import subprocess
 from tempfile import TemporaryFile

@@ -3,9 +3,7 @@
    python tests/tools/vbx_profile.py [minutes]"""
 import os
 import sys
-import time
 
-import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
